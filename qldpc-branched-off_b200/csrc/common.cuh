@@ -1,0 +1,141 @@
+// Internal declarations shared by the .cu files of libqldpc_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qldpc_b200.h"
+
+namespace qb {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define QB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return qb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define QB_REQUIRE(cond, msg)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            qb::set_error(msg);               \
+            return QB_ERR_ARG;                \
+        }                                     \
+    } while (0)
+
+// Grow-only device scratch buffer owned by a handle.
+struct Scratch {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T *as() { return reinterpret_cast<T *>(ptr); }
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int MS_THREADS = 512;      // min-sum CTA size (16 warps)
+constexpr int MS_MAX_ROW_DEG = 57;   // sign bits + argmin + total sign must fit two 32-bit words
+constexpr int OSD_THREADS = 512;
+constexpr int OSD_MAX_WPL = 4;       // syndrome words per lane -> m <= 4096
+
+// Device view of one decoding side (what kernels receive by value).
+struct GraphDev {
+    int m, n, nnz, k, mw, nw, m_pad, n_pad;
+    int n_rslices, n_cslices;
+    // sliced ELL, 32 rows / 32 columns per slice, slice s occupies [ptr[s], ptr[s+1]) entries,
+    // entry (t, lane) at ptr[s] + 32*t + lane
+    const int32_t *rslice_ptr;
+    const uint16_t *row_ell;    // column index, 0xFFFF = padding
+    const int32_t *cslice_ptr;
+    const uint32_t *col_ell;    // check << 8 | position in row, 0xFFFFFFFF = padding
+    // plain CSR / CSC (general kernels, OSD)
+    const int32_t *indptr, *indices;           // CSR
+    const int32_t *colptr, *rowidx, *csc_edge; // CSC: row index and CSR edge id of each entry
+    const float *prior;
+    const uint32_t *logmask;                   // per column: bit b = logical row b contains the column
+};
+
+}  // namespace qb
+
+struct qb_decoder {
+    int device = 0;
+    qb::GraphDev g{};
+    int max_row_deg = 0, max_col_deg = 0;
+    bool fast_ok = false;       // fast (on-chip message) min-sum kernel applicable
+    std::vector<int32_t> h_indptr, h_indices, h_colptr, h_rowidx;
+    std::vector<void *> owned;  // device allocations freed on destroy
+    float *d_prior = nullptr;
+    float *d_alpha = nullptr;   // per-iteration alpha, device
+    int alpha_cap = 0;
+    qb::Scratch scratch;        // host-API staging
+    qb::Scratch work;           // kernel workspaces (general min-sum messages, OSD spill)
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+struct qb_sampler {
+    int device = 0;
+    int L = 0, k = 0;
+    int mZ = 0, nZ = 0, mX = 0, nX = 0, mwZ = 0, mwX = 0;
+    int8_t *d_kind = nullptr;
+    int32_t *d_colZ = nullptr, *d_colX = nullptr;        // [L][4]
+    // column signatures: 8 x uint16 per column: up to 7 rows (0xFFFF = none) ... or CSC when wider
+    int32_t *d_cpZ = nullptr, *d_rowZ = nullptr, *d_cpX = nullptr, *d_rowX = nullptr;
+    uint32_t *d_lmZ = nullptr, *d_lmX = nullptr;
+    std::vector<void *> owned;
+    qb::Scratch scratch;
+    int sm_count = 148;
+};
+
+namespace qb {
+
+// ---- launchers implemented in the individual .cu files --------------------------------------------
+struct MinsumLaunch {
+    const uint32_t *syn_bits;
+    int B, max_iter;
+    const float *alpha_d;       // [max_iter]
+    float damping, clip;
+    int dense_variant;
+    uint32_t *hard_bits;
+    uint8_t *converged;
+    int32_t *final_iter;
+    float *post;                // nullable [B][n]
+    int post_failed_only;       // write post only for non-converged shots
+    int32_t *fail_count;        // nullable: device counter, non-converged shots are appended
+    int32_t *fail_idx;
+};
+int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st);
+int upload_alpha(qb_decoder *dec, int max_iter, int alpha_mode, double alpha, const double *seq, int len,
+                 cudaStream_t st);
+
+struct OsdLaunch {
+    const uint32_t *syn_bits;   // [B][mw]
+    uint32_t *hard_bits;        // [B][nw] in/out
+    const float *post;          // [B][n] (used when ordering == nullptr)
+    const int32_t *ordering;    // nullable [B][n]: caller-supplied column orders
+    const int32_t *fail_idx;    // nullable: indices into the batch; nullptr = all of 0..F-1
+    int F;                      // number of sides (upper bound when n_fail_d given)
+    const int32_t *n_fail_d;    // nullable device count
+    int32_t *rank_out;          // nullable [B]
+    int32_t *pivots_out;        // nullable [B][min(m,n)]
+};
+int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
+
+int launch_events_syndrome(qb_sampler *s, const int32_t *ev_ptr_d, const uint32_t *events_d, int B,
+                           uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX, cudaStream_t st);
+int launch_sample_syndrome(qb_sampler *s, uint64_t seed, uint64_t first_shot, int B, double p,
+                           uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX,
+                           int32_t *nfaults, cudaStream_t st);
+
+// bit packing helpers (device kernels, utils.cu)
+int launch_pack_bits(const int8_t *src, int B, int len, uint32_t *dst, int words, cudaStream_t st);
+int launch_unpack_bits(const uint32_t *src, int B, int len, int words, int8_t *dst, cudaStream_t st);
+int launch_logical_check(const qb_decoder *dec, const uint32_t *hard_bits, const uint32_t *true_mask, int B,
+                         uint8_t *flags, int flag_bit, int64_t *counts, int count_slot, cudaStream_t st);
+
+}  // namespace qb

@@ -1,0 +1,562 @@
+// K3: batched flooding min-sum (and the rarely used general / tanh-BP / single-pass variants).
+//
+// Reference semantics: src/decoding/kernels.py:235-366 (minsum_decoder_full), :370-485
+// (autoregressive alpha), :139-169 (minsum_core_sparse), :172-193 + dense.py:75-96 (tanh BP).
+//
+// Fast kernel (damping == 1, which is every call the engine makes, engine.py:84-88):
+//   * one CTA owns S shots of one side; all per-shot state lives in shared memory:
+//       posterior values  float [n_pad][S]           (shot-interleaved -> one LDS.128 per edge for S=4)
+//       check state       uint4 [S][m_pad]           {alpha*min1, alpha*min2, signs 0..31,
+//                                                      signs 32..56 | argmin<<25 | total sign<<31}
+//     Because damping == 1 the variable-to-check message is  clip(value[j] - R_old(edge)) and
+//     R_old is recomputed from the compressed check state, so no per-edge message is stored.
+//   * phase A: one thread per check row walks the row's sliced-ELL column list (coalesced uint16
+//     loads, the graph is shared by the S shots) and produces the new compressed state;
+//   * phase B: one thread per variable gathers its <=6 check states in row order (same summation
+//     order as the reference), adds the prior, and XORs its checks' parity bits when the hard
+//     decision is 1, which yields the convergence test without another pass over the graph.
+// IEEE inf/NaN behaviour is kept (no fast-math): degree-1 checks produce +-inf messages and
+// inf-inf = NaN -> 0 exactly like kernels.py:327-329.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qb {
+
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(MS_THREADS, 1)
+minsum_fast_kernel(GraphDev g, MinsumLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *vals = reinterpret_cast<float *>(smem_raw);                               // [n_pad][S]
+    uint4 *chk = reinterpret_cast<uint4 *>(smem_raw + (size_t)g.n_pad * S * sizeof(float));  // [S][m_pad]
+    uint32_t *syn = reinterpret_cast<uint32_t *>(chk + (size_t)S * g.m_pad);        // [S][mw]
+    uint32_t *par = syn + S * g.mw;                                                  // [S][mw]
+    __shared__ int s_unsat[S];
+    __shared__ int s_active[S];
+    __shared__ int s_nactive;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float clip = a.clip;
+    const int n_tiles = (a.B + S - 1) / S;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int shot0 = tile * S;
+        // ---- load: values = prior, syndrome words, parity = 0 ---------------------------------
+        for (int j = tid; j < g.n_pad; j += blockDim.x) {
+            float p = j < g.n ? g.prior[j] : 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) vals[j * S + s] = p;
+        }
+        for (int i = tid; i < S * g.mw; i += blockDim.x) {
+            int s = i / g.mw, w = i - s * g.mw;
+            syn[i] = (shot0 + s < a.B) ? a.syn_bits[(size_t)(shot0 + s) * g.mw + w] : 0u;
+            par[i] = 0u;
+        }
+        if (tid < S) { s_active[tid] = (shot0 + tid < a.B); s_unsat[tid] = 0; }
+        if (tid == 0) s_nactive = min(S, a.B - shot0);
+        __syncthreads();
+        if (a.max_iter <= 0) {
+            // reference returns all-zero candidate, converged False, final_iter -1 (kernels.py:267)
+            for (int s = 0; s < S; ++s) {
+                if (shot0 + s >= a.B) break;
+                size_t shot = shot0 + s;
+                for (int w = tid; w < g.nw; w += blockDim.x) a.hard_bits[shot * g.nw + w] = 0u;
+                if (a.post) for (int j = tid; j < g.n; j += blockDim.x) a.post[shot * g.n + j] = 0.f;
+                if (tid == 0) {
+                    a.converged[shot] = 0; a.final_iter[shot] = -1;
+                    if (a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = (int)shot;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+
+        for (int it = 0; it < a.max_iter; ++it) {
+            const float alpha = a.alpha_d[it];
+            bool act[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) act[s] = s_active[s] != 0;
+
+            // ---- phase A: check rows ----------------------------------------------------------
+            for (int rs = warp; rs < g.n_rslices; rs += nwarps) {
+                const int base = g.rslice_ptr[rs];
+                const int deg = (g.rslice_ptr[rs + 1] - base) >> 5;
+                const int r = rs * 32 + lane;
+                float o1[S], o2[S];
+                unsigned long long osg[S];
+                int oam[S];
+                uint32_t otot[S];
+                float mn1[S], mn2[S];
+                unsigned long long nsg[S];
+                int am[S];
+                uint32_t npar[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    mn1[s] = INFINITY; mn2[s] = INFINITY; nsg[s] = 0ull; am[s] = 0; npar[s] = 0u;
+                    if (it > 0) {
+                        uint4 st = chk[s * g.m_pad + r];
+                        o1[s] = __uint_as_float(st.x); o2[s] = __uint_as_float(st.y);
+                        osg[s] = (unsigned long long)st.z | ((unsigned long long)(st.w & 0x01FFFFFFu) << 32);
+                        oam[s] = (st.w >> 25) & 63; otot[s] = st.w >> 31;
+                    } else {
+                        o1[s] = 0.f; o2[s] = 0.f; osg[s] = 0ull; oam[s] = -1; otot[s] = 0u;
+                    }
+                }
+                for (int t = 0; t < deg; ++t) {
+                    const uint32_t j = g.row_ell[base + t * 32 + lane];
+                    if (j != 0xFFFFu) {
+                        float v[S];
+                        if constexpr (S == 4) {
+                            float4 f = *reinterpret_cast<const float4 *>(vals + j * 4);
+                            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                        } else if constexpr (S == 2) {
+                            float2 f = *reinterpret_cast<const float2 *>(vals + j * 2);
+                            v[0] = f.x; v[1] = f.y;
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < S; ++s) v[s] = vals[j * S + s];
+                        }
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            if (!act[s]) continue;
+                            float q = v[s];
+                            if (it > 0) {
+                                float omag = (t == oam[s]) ? o2[s] : o1[s];
+                                uint32_t osgn = ((uint32_t)(osg[s] >> t) & 1u) ^ otot[s];
+                                float rold = osgn ? -omag : omag;
+                                q = v[s] - rold;
+                                if (q != q) q = 0.f;                 // kernels.py:328-329
+                                else q = fminf(fmaxf(q, -clip), clip);
+                            }
+                            const uint32_t neg = (q < 0.f) ? 1u : 0u;   // val >= 0 -> '+', kernels.py:296
+                            nsg[s] |= (unsigned long long)neg << t;
+                            npar[s] ^= neg;
+                            const float ab = fabsf(q);
+                            am[s] = (ab < mn1[s]) ? t : am[s];         // strict <: first minimum wins
+                            mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
+                            mn1[s] = fminf(mn1[s], ab);
+                        }
+                    }
+                }
+                if (r < g.m) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (!act[s]) continue;
+                        uint32_t sbit = (syn[s * g.mw + (r >> 5)] >> (r & 31)) & 1u;
+                        uint32_t tot = sbit ^ npar[s];
+                        uint4 st;
+                        st.x = __float_as_uint(alpha * mn1[s]);
+                        st.y = __float_as_uint(alpha * mn2[s]);
+                        st.z = (uint32_t)nsg[s];
+                        st.w = ((uint32_t)(nsg[s] >> 32) & 0x01FFFFFFu) | ((uint32_t)am[s] << 25) | (tot << 31);
+                        chk[s * g.m_pad + r] = st;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase B: variables ------------------------------------------------------------
+            for (int cs = warp; cs < g.n_cslices; cs += nwarps) {
+                const int base = g.cslice_ptr[cs];
+                const int deg = (g.cslice_ptr[cs + 1] - base) >> 5;
+                const int j = cs * 32 + lane;
+                float acc[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) acc[s] = 0.f;
+                for (int t = 0; t < deg; ++t) {
+                    const uint32_t e = g.col_ell[base + t * 32 + lane];
+                    if (e != 0xFFFFFFFFu) {
+                        const int c = e >> 8, pos = e & 255;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            if (!act[s]) continue;
+                            const uint4 st = chk[s * g.m_pad + c];
+                            const float mag = (pos == (int)((st.w >> 25) & 63)) ? __uint_as_float(st.y) : __uint_as_float(st.x);
+                            const uint32_t word = pos < 32 ? st.z : st.w;
+                            const uint32_t sgn = ((word >> (pos & 31)) & 1u) ^ (st.w >> 31);
+                            acc[s] += sgn ? -mag : mag;            // R_sum[col] += msg, kernels.py:316
+                        }
+                    }
+                }
+                if (j < g.n) {
+                    const float pr = g.prior[j];
+                    uint32_t negmask = 0u;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (!act[s]) continue;
+                        const float v = acc[s] + pr;               // kernels.py:320
+                        vals[j * S + s] = v;
+                        if (v < 0.f) negmask |= 1u << s;           // kernels.py:349
+                    }
+                    if (negmask) {
+                        for (int t = 0; t < deg; ++t) {
+                            const uint32_t e = g.col_ell[base + t * 32 + lane];
+                            if (e == 0xFFFFFFFFu) break;
+                            const int c = e >> 8;
+#pragma unroll
+                            for (int s = 0; s < S; ++s)
+                                if (negmask & (1u << s)) atomicXor(&par[s * g.mw + (c >> 5)], 1u << (c & 31));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- convergence: H.hard == syndrome  (kernels.py:352-364) ---------------------------
+            for (int i = tid; i < S * g.mw; i += blockDim.x) {
+                if (par[i] != syn[i]) s_unsat[i / g.mw] = 1;
+                par[i] = 0u;
+            }
+            __syncthreads();
+            const bool last = (it == a.max_iter - 1);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                if (!act[s]) continue;
+                const bool conv = (s_unsat[s] == 0);
+                if (conv || last) {
+                    const size_t shot = shot0 + s;
+                    for (int j = tid; j < g.n_pad; j += blockDim.x) {
+                        const float v = vals[j * S + s];
+                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, j < g.n && v < 0.f);
+                        if (lane == 0 && (j >> 5) < g.nw) a.hard_bits[shot * g.nw + (j >> 5)] = word;
+                        if (a.post && j < g.n && !(a.post_failed_only && conv)) a.post[shot * g.n + j] = v;
+                    }
+                    if (tid == 0) {
+                        a.converged[shot] = conv ? 1 : 0;
+                        a.final_iter[shot] = it;
+                        if (!conv && a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = (int)shot;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int na = 0;
+                for (int s = 0; s < S; ++s) {
+                    if (s_active[s] && (s_unsat[s] == 0 || last)) s_active[s] = 0;
+                    s_unsat[s] = 0;
+                    na += s_active[s];
+                }
+                s_nactive = na;
+            }
+            __syncthreads();
+            if (s_nactive == 0) break;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// General kernel: per-edge messages in global memory, any degree, damping != 1, dense.py variant.
+// One CTA per shot slot; ws holds per-slot Q[nnz], R[nnz], values[n] floats.
+__global__ void __launch_bounds__(256)
+minsum_general_kernel(GraphDev g, MinsumLaunch a, float *ws)
+{
+    extern __shared__ uint32_t sm_words[];
+    uint32_t *syn = sm_words, *par = sm_words + g.mw;
+    __shared__ int s_unsat;
+    const int tid = threadIdx.x;
+    float *Q = ws + (size_t)blockIdx.x * (2 * (size_t)g.nnz + g.n);
+    float *R = Q + g.nnz;
+    float *vals = R + g.nnz;
+    const float clip = a.clip, damping = a.damping;
+
+    for (int shot = blockIdx.x; shot < a.B; shot += gridDim.x) {
+        for (int e = tid; e < g.nnz; e += blockDim.x) Q[e] = g.prior[g.indices[e]];
+        for (int j = tid; j < g.n; j += blockDim.x) vals[j] = 0.f;
+        for (int w = tid; w < g.mw; w += blockDim.x) { syn[w] = a.syn_bits[(size_t)shot * g.mw + w]; par[w] = 0u; }
+        if (tid == 0) s_unsat = 0;
+        __syncthreads();
+        int fin = a.max_iter - 1;
+        bool conv = false;
+        for (int it = 0; it < a.max_iter; ++it) {
+            const float alpha = a.alpha_d[it];
+            for (int r = tid; r < g.m; r += blockDim.x) {
+                const int rs = g.indptr[r], re = g.indptr[r + 1];
+                if (rs == re) continue;
+                uint32_t tot = (syn[r >> 5] >> (r & 31)) & 1u;
+                float mn1 = INFINITY, mn2 = INFINITY;
+                int mp = -1;
+                for (int e = rs; e < re; ++e) {
+                    const float q = Q[e];
+                    tot ^= (q >= 0.f) ? 0u : 1u;
+                    const float ab = fabsf(q);
+                    if (ab < mn1) { mn2 = mn1; mn1 = ab; mp = e; } else if (ab < mn2) mn2 = ab;
+                }
+                const float a1 = alpha * mn1, a2 = alpha * mn2;
+                for (int e = rs; e < re; ++e) {
+                    const uint32_t sg = tot ^ ((Q[e] >= 0.f) ? 0u : 1u);
+                    const float mag = (e == mp) ? a2 : a1;
+                    R[e] = sg ? -mag : mag;
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < g.n; j += blockDim.x) {
+                float acc = 0.f;
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) acc += R[g.csc_edge[p]];
+                const float v = acc + g.prior[j];
+                vals[j] = v;
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) {
+                    const int e = g.csc_edge[p];
+                    float q = v - R[e];
+                    if (q != q) q = 0.f;
+                    else if (a.dense_variant) { if (isinf(q)) q = q > 0.f ? clip : -clip; }
+                    else q = fminf(fmaxf(q, -clip), clip);
+                    float qd = damping * q + (1.0f - damping) * Q[e];
+                    qd = fminf(fmaxf(qd, -clip), clip);
+                    Q[e] = qd;
+                    if (v < 0.f) { const int c = g.rowidx[p]; atomicXor(&par[c >> 5], 1u << (c & 31)); }
+                }
+            }
+            __syncthreads();
+            for (int w = tid; w < g.mw; w += blockDim.x) { if (par[w] != syn[w]) s_unsat = 1; par[w] = 0u; }
+            __syncthreads();
+            const bool ok = (s_unsat == 0);
+            __syncthreads();
+            if (tid == 0) s_unsat = 0;
+            if (ok) { fin = it; conv = true; break; }
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < g.n_pad; j0 += blockDim.x) {
+            const int j = j0 + tid;
+            const float v = j < g.n ? vals[j] : 0.f;
+            const bool neg = (a.max_iter > 0) && j < g.n && v < 0.f;
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, neg);
+            if ((tid & 31) == 0 && (j >> 5) < g.nw) a.hard_bits[(size_t)shot * g.nw + (j >> 5)] = word;
+            if (a.post && j < g.n && !(a.post_failed_only && conv)) a.post[(size_t)shot * g.n + j] = v;
+        }
+        if (tid == 0) {
+            a.converged[shot] = conv ? 1 : 0;
+            a.final_iter[shot] = fin;
+            if (!conv && a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = shot;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// minsum_core_sparse (kernels.py:139-169), double precision (used by the alpha estimators).
+__global__ void minsum_core_kernel(GraphDev g, const double *Q, const double *ssign, int B, double alpha,
+                                   double *R, double *Rsum)
+{
+    const int shot = blockIdx.x;
+    const double *q = Q + (size_t)shot * g.nnz;
+    double *r_ = R + (size_t)shot * g.nnz;
+    for (int r = threadIdx.x; r < g.m; r += blockDim.x) {
+        const int rs = g.indptr[r], re = g.indptr[r + 1];
+        if (rs == re) continue;
+        double sp = ssign[(size_t)shot * g.m + r], mn1 = INFINITY, mn2 = INFINITY;
+        int mp = -1;
+        for (int e = rs; e < re; ++e) {
+            const double v = q[e];
+            sp *= (v >= 0) ? 1.0 : -1.0;
+            const double ab = fabs(v);
+            if (ab < mn1) { mn2 = mn1; mn1 = ab; mp = e; } else if (ab < mn2) mn2 = ab;
+        }
+        for (int e = rs; e < re; ++e) {
+            const double sj = (q[e] >= 0) ? 1.0 : -1.0;
+            r_[e] = alpha * (sp * sj) * ((e == mp) ? mn2 : mn1);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < g.n; j += blockDim.x) {
+        double acc = 0.0;
+        for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) acc += r_[g.csc_edge[p]];
+        Rsum[(size_t)shot * g.n + j] = acc;
+    }
+}
+
+// tanh/atanh BP (dense.py:75-96, kernels.py:172-193), double precision; ws per slot: Q[nnz], R[nnz], vals[n]
+__global__ void __launch_bounds__(256)
+bp_kernel(GraphDev g, const uint32_t *syn_bits, int B, int max_iter, uint32_t *hard_bits, uint8_t *converged,
+          int32_t *final_iter, double *post, double *ws)
+{
+    extern __shared__ uint32_t sm_words[];
+    uint32_t *syn = sm_words, *par = sm_words + g.mw;
+    __shared__ int s_unsat;
+    const int tid = threadIdx.x;
+    double *Q = ws + (size_t)blockIdx.x * (2 * (size_t)g.nnz + g.n);
+    double *R = Q + g.nnz;
+    double *vals = R + g.nnz;
+    const double CLIP = 0.9999999;
+    for (int shot = blockIdx.x; shot < B; shot += gridDim.x) {
+        for (int e = tid; e < g.nnz; e += blockDim.x) Q[e] = (double)g.prior[g.indices[e]];
+        for (int j = tid; j < g.n; j += blockDim.x) vals[j] = 0.0;
+        for (int w = tid; w < g.mw; w += blockDim.x) { syn[w] = syn_bits[(size_t)shot * g.mw + w]; par[w] = 0u; }
+        if (tid == 0) s_unsat = 0;
+        __syncthreads();
+        int fin = max_iter - 1;
+        bool conv = false;
+        for (int it = 0; it < max_iter; ++it) {
+            for (int r = tid; r < g.m; r += blockDim.x) {
+                const double ss = ((syn[r >> 5] >> (r & 31)) & 1u) ? -1.0 : 1.0;
+                double prod = 1.0;
+                for (int e = g.indptr[r]; e < g.indptr[r + 1]; ++e) {
+                    double t = tanh(Q[e] * 0.5);
+                    if (fabs(t) < 1e-15) t = (t >= 0) ? 1e-15 : -1e-15;
+                    prod *= t;
+                }
+                for (int e = g.indptr[r]; e < g.indptr[r + 1]; ++e) {
+                    double t = tanh(Q[e] * 0.5);
+                    if (fabs(t) < 1e-15) t = (t >= 0) ? 1e-15 : -1e-15;
+                    double po = prod / t * ss;
+                    po = fmin(fmax(po, -CLIP), CLIP);
+                    R[e] = 2.0 * atanh(po);
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < g.n; j += blockDim.x) {
+                double acc = 0.0;
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) acc += R[g.csc_edge[p]];
+                const double v = acc + (double)g.prior[j];
+                vals[j] = v;
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) {
+                    const int e = g.csc_edge[p];
+                    Q[e] = v - R[e];
+                    if (v < 0) { const int c = g.rowidx[p]; atomicXor(&par[c >> 5], 1u << (c & 31)); }
+                }
+            }
+            __syncthreads();
+            for (int w = tid; w < g.mw; w += blockDim.x) { if (par[w] != syn[w]) s_unsat = 1; par[w] = 0u; }
+            __syncthreads();
+            const bool ok = (s_unsat == 0);
+            __syncthreads();
+            if (tid == 0) s_unsat = 0;
+            if (ok) { fin = it; conv = true; break; }
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < g.n_pad; j0 += blockDim.x) {
+            const int j = j0 + tid;
+            const double v = j < g.n ? vals[j] : 0.0;
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, max_iter > 0 && j < g.n && v < 0);
+            if ((tid & 31) == 0 && (j >> 5) < g.nw) hard_bits[(size_t)shot * g.nw + (j >> 5)] = word;
+            if (post && j < g.n) post[(size_t)shot * g.n + j] = v;
+        }
+        if (tid == 0) { converged[shot] = conv ? 1 : 0; final_iter[shot] = fin; }
+        __syncthreads();
+    }
+}
+
+// H.candidate mod 2 (syndrome_check, kernels.py:223-231): one warp per (shot, 32 rows)
+__global__ void syndrome_check_kernel(GraphDev g, const uint32_t *cand_bits, int B, uint32_t *syn_bits)
+{
+    const int shot = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = 0;
+    if (r < g.m)
+        for (int e = g.indptr[r]; e < g.indptr[r + 1]; ++e) {
+            const int j = g.indices[e];
+            s ^= (cand_bits[(size_t)shot * g.nw + (j >> 5)] >> (j & 31)) & 1u;
+        }
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, s != 0);
+    if ((threadIdx.x & 31) == 0 && (r >> 5) < g.mw) syn_bits[(size_t)shot * g.mw + (r >> 5)] = word;
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t fast_smem_bytes(const GraphDev &g, int S)
+{
+    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4;
+}
+
+int fast_shots_per_cta(const qb_decoder *dec)
+{
+    if (!dec->fast_ok) return 0;
+    const int cand[3] = {4, 2, 1};
+    for (int S : cand)
+        if (fast_smem_bytes(dec->g, S) + 1024 <= (size_t)dec->max_smem_optin) return S;
+    return 0;
+}
+
+template <int S>
+static int launch_fast(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
+{
+    const size_t smem = fast_smem_bytes(dec->g, S);
+    QB_CUDA(cudaFuncSetAttribute(minsum_fast_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (a.B + S - 1) / S;
+    int ctas_per_sm = std::max(1, std::min(4, (int)((size_t)dec->max_smem_optin / (smem + 1024))));
+    // thread count: enough warps for the slices, fewer for small codes so several CTAs share an SM
+    int threads = MS_THREADS;
+    if (ctas_per_sm >= 2) threads = 256;
+    ctas_per_sm = std::min(ctas_per_sm, 2048 / threads);
+    const int grid = std::max(1, std::min(tiles, dec->sm_count * ctas_per_sm));
+    minsum_fast_kernel<S><<<grid, threads, smem, st>>>(dec->g, a);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
+{
+    if (a.B <= 0) return QB_OK;
+    const int S = (a.damping == 1.0f) ? fast_shots_per_cta(dec) : 0;
+    if (S == 4) return launch_fast<4>(dec, a, st);
+    if (S == 2) return launch_fast<2>(dec, a, st);
+    if (S == 1) return launch_fast<1>(dec, a, st);
+    // general path
+    const GraphDev &g = dec->g;
+    const int slots = std::max(1, std::min(a.B, dec->sm_count * 4));
+    const size_t per = (2 * (size_t)g.nnz + g.n) * sizeof(float);
+    if (int rc = dec->work.ensure(per * slots)) return rc;
+    minsum_general_kernel<<<slots, 256, 2 * g.mw * sizeof(uint32_t), st>>>(g, a, dec->work.as<float>());
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_minsum_core(qb_decoder *dec, const double *Q, const double *ssign, int B, double alpha, double *R,
+                       double *Rsum, cudaStream_t st)
+{
+    if (B <= 0) return QB_OK;
+    minsum_core_kernel<<<B, 256, 0, st>>>(dec->g, Q, ssign, B, alpha, R, Rsum);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_bp(qb_decoder *dec, const uint32_t *syn_bits, int B, int max_iter, uint32_t *hard_bits,
+              uint8_t *converged, int32_t *final_iter, double *post, cudaStream_t st)
+{
+    if (B <= 0) return QB_OK;
+    const GraphDev &g = dec->g;
+    const int slots = std::max(1, std::min(B, dec->sm_count * 4));
+    const size_t per = (2 * (size_t)g.nnz + g.n) * sizeof(double);
+    if (int rc = dec->work.ensure(per * slots)) return rc;
+    bp_kernel<<<slots, 256, 2 * g.mw * sizeof(uint32_t), st>>>(g, syn_bits, B, max_iter, hard_bits, converged,
+                                                               final_iter, post, dec->work.as<double>());
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_syndrome_check(qb_decoder *dec, const uint32_t *cand_bits, int B, uint32_t *syn_bits, cudaStream_t st)
+{
+    if (B <= 0) return QB_OK;
+    dim3 grid(ceil_div(dec->g.m_pad, 128), B);
+    syndrome_check_kernel<<<grid, 128, 0, st>>>(dec->g, cand_bits, B, syn_bits);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int upload_alpha(qb_decoder *dec, int max_iter, int alpha_mode, double alpha, const double *seq, int len,
+                 cudaStream_t st)
+{
+    const int n = std::max(1, max_iter);
+    if (n > dec->alpha_cap) {
+        if (dec->d_alpha) cudaFree(dec->d_alpha);
+        dec->d_alpha = nullptr;
+        QB_CUDA(cudaMalloc(&dec->d_alpha, sizeof(float) * n));
+        dec->alpha_cap = n;
+    }
+    std::vector<float> h(n);
+    for (int it = 0; it < n; ++it) {
+        double v;
+        if (alpha_mode == QB_ALPHA_DYNAMIC) v = 1.0 - pow(2.0, -(double)(it + 1));       // kernels.py:273
+        else if (alpha_mode == QB_ALPHA_SEQUENCE) v = seq[it < len ? it : len - 1];        // kernels.py:402-405
+        else v = alpha;
+        h[it] = (float)v;
+    }
+    QB_CUDA(cudaMemcpyAsync(dec->d_alpha, h.data(), sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    QB_CUDA(cudaStreamSynchronize(st));   // h goes out of scope
+    return QB_OK;
+}
+
+}  // namespace qb

@@ -1,0 +1,191 @@
+"""``run_simulation`` on the GPU (reference ``src/simulation/engine.py:193-488``).
+
+Same keyword arguments and result dict.  Differences that do not change semantics:
+  * shots run in device batches through the fused pipeline (sample -> syndromes -> min-sum ->
+    OSD-0 -> logical check) instead of a process pool; ``num_workers`` / ``use_jit`` are accepted
+    and ignored;
+  * the per-shot generator is Philox4x32-10 keyed by ``base_seed`` with the shot index as counter
+    (reference: MT19937 reseeded per shot, engine.py:70), so results are reproducible and do not
+    depend on the batch size or the number of GPUs; LERs agree statistically;
+  * early stop (``target_logical_errors``) is replayed on the host over per-shot flags in shot
+    order, which gives the reference's exact cut (engine.py:450-464);
+  * with ``torch.distributed`` initialised every rank takes a contiguous slice of each round of
+    shots and the counters are all-reduced (NCCL on GPUs, gloo in the CPU tests).
+"""
+import logging
+
+import numpy as np
+
+from .. import _lib
+from ..codes.bb_code import BBCodeCircuit
+from ..noise.builder import fault_tables_for, matrices_from_tables
+from ..noise.compiled import CompiledCircuit
+
+_logger = logging.getLogger(__name__)
+
+
+def llr_priors(channel_probs):
+    """engine.py:210-212."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cp = np.asarray(channel_probs, dtype=np.float64)
+        return np.clip(np.nan_to_num(np.log((1 - cp) / cp)), -50, 50)
+
+
+def _dense_to_csr(H):
+    mask = np.asarray(H) != 0
+    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
+    return indptr, np.nonzero(mask)[1].astype(np.int32)
+
+
+def shard_range(total, rank, world):
+    """Contiguous slice [lo, hi) of ``total`` items owned by ``rank`` (sizes differ by at most 1)."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def early_stop_cut(flags, target, errors_before=0):
+    """Index (exclusive) at which the reference loop stops: first shot where the cumulative number
+    of logical errors reaches ``target`` (engine.py:450-464); None if not reached in ``flags``."""
+    cum = errors_before + np.cumsum(np.asarray(flags) != 0)
+    hit = np.nonzero(cum >= target)[0]
+    return None if hit.size == 0 else int(hit[0]) + 1
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return None, 0, 1
+
+
+class ShotEngine:
+    """Device state of one (code, p): sampler, two decoders, pipeline."""
+
+    def __init__(self, compiled, Lx, Lz, matrices, max_batch=16384, device=None):
+        ft = fault_tables_for(compiled, Lx, Lz)
+        self.ft = ft
+        k = np.asarray(Lx).shape[0]
+        mz, mx = int(matrices["first_logical_rowZ"]), int(matrices["first_logical_rowX"])
+        self.llrs_z = llr_priors(matrices["channel_probsZ"])
+        self.llrs_x = llr_priors(matrices["channel_probsX"])
+        HZf, HXf = np.asarray(matrices["HZ_full"]), np.asarray(matrices["HX_full"])
+        zp, zi = _dense_to_csr(matrices["HdecZ"])
+        xp, xi = _dense_to_csr(matrices["HdecX"])
+        self.nnz = (len(zi), len(xi))
+        self.sampler = _lib.Sampler(ft, device)
+        self.decZ = _lib.Decoder(zp, zi, np.asarray(matrices["HdecZ"]).shape[1], self.llrs_z, HZf[mz:mz + k], device)
+        self.decX = _lib.Decoder(xp, xi, np.asarray(matrices["HdecX"]).shape[1], self.llrs_x, HXf[mx:mx + k], device)
+        self.pipeline = _lib.Pipeline(self.sampler, self.decZ, self.decX, max_batch)
+        self.max_batch = max_batch
+
+    def close(self):
+        self.pipeline.close(); self.decZ.close(); self.decX.close(); self.sampler.close()
+
+
+def _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha):
+    if alpha_mode is None:
+        alpha_mode = "dynamical" if use_dynamic_alpha else "alvarado"
+    if alpha_mode == "dynamical":
+        return alpha_mode, _lib.QB_ALPHA_DYNAMIC, 1.0, 1.0
+    if alpha_mode == "alvarado":
+        if alvarado_alpha is None:
+            raise NotImplementedError("Alvarado alpha estimation pre-pass (reference src/decoding/alpha.py) is not part "
+                                      "of the GPU hot path yet; pass alvarado_alpha=(alpha_z, alpha_x)")
+        if isinstance(alvarado_alpha, (list, tuple, np.ndarray)) and len(alvarado_alpha) == 2:
+            az, ax = float(alvarado_alpha[0]), float(alvarado_alpha[1])
+        else:
+            az = ax = float(alvarado_alpha)
+        if az <= 0 or ax <= 0:
+            raise ValueError("alpha must be > 0 when alpha_mode='alvarado'")
+        return alpha_mode, _lib.QB_ALPHA_FIXED, az, ax
+    if alpha_mode == "alvarado-autoregressive":
+        if alvarado_alpha is not None:
+            raise ValueError("alvarado_alpha must be None for alvarado-autoregressive")
+        raise NotImplementedError("autoregressive alpha estimation pre-pass (reference src/decoding/alpha.py:160-276) "
+                                  "is not part of the GPU hot path yet; use run_shots(alpha_seq_z=..., alpha_seq_x=...)")
+    raise ValueError(f"Unsupported alpha_mode: {alpha_mode}")
+
+
+def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, maxIter=50, osd_order=0,
+                   use_dynamic_alpha=True, alpha_mode=None, alvarado_alpha=None, alpha_estimation_trials=5000,
+                   alpha_estimation_bins=50, precomputed_matrices=None, num_workers=None, base_seed=None,
+                   use_jit=True, target_logical_errors=None, max_trials=None, scopt=False,
+                   estimation_plot_dir=None, batch_size=None, **bb_params):
+    if scopt:
+        raise NotImplementedError("SCOPT beta estimation (reference scopt.py) is outside the GPU hot path")
+    if base_seed is None:
+        base_seed = np.random.randint(0, 2 ** 31)
+    alpha_mode, qmode, alpha_z, alpha_x = _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha)
+    cb = BBCodeCircuit(Hx, Hz, num_cycles=num_cycles, **bb_params)
+    compiled = CompiledCircuit.from_builder(cb)
+    ft = fault_tables_for(compiled, Lx, Lz)
+    matrices = precomputed_matrices or matrices_from_tables(ft, error_rate, num_cycles)
+    if max_trials is None:
+        max_trials = num_trials if num_trials is not None else 1000000
+    stop_on_errors = target_logical_errors is not None and target_logical_errors > 0
+
+    dist, rank, world = _dist()
+    if batch_size is None:
+        batch_size = int(min(16384, max(256, -(-max_trials // world))))
+    eng = ShotEngine(compiled, Lx, Lz, matrices, max_batch=batch_size)
+    cfg = _lib.make_config(maxIter, qmode, alpha_z, alpha_x, clip_llr=20.0, use_osd=True)
+    try:
+        z_errs = x_errs = tot_errs = trials_run = 0
+        done = 0
+        while done < max_trials:
+            round_total = min(world * batch_size, max_trials - done)
+            lo, hi = shard_range(round_total, rank, world)
+            counts, flags = eng.pipeline.run(base_seed, done + lo, hi - lo, error_rate, cfg, want_flags=stop_on_errors)
+            if stop_on_errors:
+                all_flags = _gather_flags(dist, world, flags, round_total)
+                cut = early_stop_cut(all_flags & 3, target_logical_errors, tot_errs)
+                use = all_flags[:cut] if cut is not None else all_flags
+                z_errs += int(np.sum(use & 1 != 0)); x_errs += int(np.sum(use & 2 != 0)); tot_errs += int(np.sum(use != 0))
+                trials_run += len(use)
+                if cut is not None:
+                    break
+            else:
+                c = _reduce_counts(dist, counts)
+                z_errs += int(c[0]); x_errs += int(c[1]); tot_errs += int(c[2]); trials_run += int(c[3])
+            done += round_total
+    finally:
+        eng.close()
+    return {
+        "logical_error_rate": tot_errs / max(1, trials_run),
+        "z_logical_error_rate": z_errs / max(1, trials_run),
+        "x_logical_error_rate": x_errs / max(1, trials_run),
+        "num_trials": trials_run,
+        "logical_errors": tot_errs,
+    }
+
+
+def _reduce_counts(dist, counts):
+    if dist is None:
+        return counts
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(np.asarray(counts, dtype=np.int64).copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def _gather_flags(dist, world, flags, round_total):
+    if dist is None:
+        return flags
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    width = -(-round_total // world)
+    buf = np.full(width, 255, dtype=np.uint8)       # 255 = padding marker
+    buf[:len(flags)] = flags
+    t = torch.from_numpy(buf).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(round_total, r, world)
+        parts.append(out[r].cpu().numpy()[:hi - lo])
+    return np.concatenate(parts)
