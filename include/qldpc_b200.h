@@ -163,6 +163,9 @@ int qb_sample_syndromes(qb_sampler *s, uint64_t seed, uint64_t first_shot, int32
  * min-sum both sides, OSD-0 on failures, logical comparison, counters. */
 int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_t max_batch, qb_pipeline **out);
 void qb_pipeline_destroy(qb_pipeline *p);
+/* Issue all pipeline work on the caller's stream (use_external != 0; e.g. torch's current stream, so
+ * that the caller's CUDA events bracket it) or back on the pipeline's own stream (use_external == 0). */
+int qb_pipeline_set_stream(qb_pipeline *p, void *stream, int use_external);
 
 /* counts_h[8] = { z_errors, x_errors, total_errors, shots, z_nonconverged, x_nonconverged,
  *                 z_iterations, x_iterations } accumulated over the call (iterations = min-sum

@@ -42,7 +42,7 @@ EXPORTS = [
     "qb_decoder_destroy", "qb_minsum_batch", "qb_minsum_decode_host", "qb_minsum_core_host", "qb_bp_decode_host",
     "qb_syndrome_check_host", "qb_osd0_batch", "qb_osd0_host", "qb_gf2_eliminate_host", "qb_sampler_create",
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
-    "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_run", "qb_pipeline_run_events_host",
+    "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
     "qb_pipeline_decode_host", "qb_pipeline_last_stats",
 ]
 
@@ -316,6 +316,12 @@ class Pipeline:
         c, keep = cfg
         check(load().qb_pipeline_decode_host(self._h, ptr(sz), ptr(tz), ptr(sx), ptr(tx), B, C.byref(c), ptr(counts), ptr(flags)))
         return counts, flags
+
+    def set_stream(self, cuda_stream=None):
+        """Issue the pipeline's work on ``cuda_stream`` (a cudaStream_t as int, e.g.
+        ``torch.cuda.current_stream().cuda_stream``); ``None`` restores the pipeline's own stream."""
+        check(load().qb_pipeline_set_stream(self._h, c_void_p(0 if cuda_stream is None else int(cuda_stream)),
+                                            0 if cuda_stream is None else 1))
 
     def stats(self):
         s = PipelineStats()

@@ -561,7 +561,8 @@ struct qb_pipeline {
     qb_sampler *s = nullptr;
     qb_decoder *dz = nullptr, *dx = nullptr;
     int max_batch = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;        // stream all pipeline work is issued on
+    cudaStream_t own_st = nullptr;    // the pipeline's own stream (default)
     uint32_t *synZ = nullptr, *synX = nullptr, *trueZ = nullptr, *trueX = nullptr, *hardZ = nullptr, *hardX = nullptr;
     uint8_t *convZ = nullptr, *convX = nullptr, *flags = nullptr;
     int32_t *itZ = nullptr, *itX = nullptr, *failZ = nullptr, *failX = nullptr, *nfail = nullptr;   // nfail[2]
@@ -688,7 +689,8 @@ int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_
     const size_t B = (size_t)max_batch;
     const GraphDev &gz = decZ->g, &gx = decX->g;
     int rc = QB_OK;
-    if (cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking) != cudaSuccess) rc = QB_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking) != cudaSuccess) rc = QB_ERR_CUDA;
+    p->st = p->own_st;
 #define AL(ptr, cnt) if (!rc) rc = dalloc(p, &p->ptr, cnt);
     AL(synZ, B * gz.mw) AL(synX, B * gx.mw) AL(trueZ, B) AL(trueX, B) AL(hardZ, B * gz.nw) AL(hardX, B * gx.nw)
     AL(convZ, B) AL(convX, B) AL(flags, B) AL(itZ, B) AL(itX, B) AL(failZ, B) AL(failX, B) AL(nfail, 2)
@@ -710,8 +712,15 @@ void qb_pipeline_destroy(qb_pipeline *p)
     for (void *q : p->owned) cudaFree(q);
     if (p->events) cudaFree(p->events);
     for (auto e : p->evs) if (e) cudaEventDestroy(e);
-    if (p->st) cudaStreamDestroy(p->st);
+    if (p->own_st) cudaStreamDestroy(p->own_st);
     delete p;
+}
+
+int qb_pipeline_set_stream(qb_pipeline *p, void *stream, int use_external)
+{
+    QB_REQUIRE(p != nullptr, "NULL argument");
+    p->st = use_external ? static_cast<cudaStream_t>(stream) : p->own_st;
+    return QB_OK;
 }
 
 int qb_pipeline_run(qb_pipeline *p, uint64_t seed, uint64_t first_shot, int64_t n_shots, double error_rate,

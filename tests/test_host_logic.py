@@ -1,0 +1,124 @@
+"""CPU tests of the host side: C-ABI exports, alpha-mode validation, sharding / early-stop logic,
+fault-event construction, and the world_size-2 (gloo) reduction path."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import code_setup
+import qldpc_b200  # noqa: F401
+from qldpc_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "qldpc_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(qb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/qldpc_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTS)
+    assert b"sm_100a" in _lib.load().qb_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _lib.load().qb_device_count() > 0:
+        pytest.skip("GPU present")
+    from scipy.sparse import identity
+    from qldpc_b200.decoding.sparse import performMinSum_Symmetric_Sparse
+    with pytest.raises(_lib.QbError):
+        performMinSum_Symmetric_Sparse(identity(3, format="csr"), np.zeros(3, np.int8), np.ones(3))
+
+
+def test_alpha_mode_validation_matches_reference():
+    from qldpc_b200.decoding.sparse import _alpha_dispatch
+    assert _alpha_dispatch(0, None)[0] == _lib.QB_ALPHA_DYNAMIC
+    assert _alpha_dispatch(0.7, None)[:2] == (_lib.QB_ALPHA_FIXED, 0.7)
+    assert _alpha_dispatch(1.0, "dynamical")[0] == _lib.QB_ALPHA_DYNAMIC
+    with pytest.raises(ValueError):
+        _alpha_dispatch(0.0, "alvarado")
+    with pytest.raises(ValueError):
+        _alpha_dispatch(1.0, "nope")
+    with pytest.raises(ValueError):
+        _alpha_dispatch(np.zeros((2, 2)), "alvarado-autoregressive")
+    with pytest.raises(ValueError):
+        _alpha_dispatch(np.zeros(0), "alvarado-autoregressive")
+    mode, _, seq = _alpha_dispatch([0.3, 0.5], "alvarado-autoregressive")
+    assert mode == _lib.QB_ALPHA_SEQUENCE and list(seq) == [0.3, 0.5]
+
+
+def test_shard_and_early_stop_logic():
+    from qldpc_b200.simulation.engine import early_stop_cut, shard_range
+    for total in (0, 1, 7, 64, 1001):
+        for world in (1, 2, 3, 8):
+            parts = [shard_range(total, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    flags = np.array([0, 1, 0, 0, 3, 2, 0, 1], dtype=np.uint8)
+    assert early_stop_cut(flags, 1) == 2
+    assert early_stop_cut(flags, 3) == 6
+    assert early_stop_cut(flags, 2, errors_before=1) == 2
+    assert early_stop_cut(flags, 5) is None
+
+
+def test_events_from_random_matches_golden():
+    from qldpc_b200.noise.simulation import events_from_random
+    g = np.load(os.path.join(ROOT, "tests", "golden", "shots_72.npz"))
+    cc = code_setup("72")["cc"]
+    p, L = float(g["p"]), cc.num_error_locs
+    for i in range(4):
+        np.random.seed(int(g["base_seed"]) + i)
+        rv = np.random.random(L); rp = np.random.randint(0, 3, L, dtype=np.int32); r2 = np.random.randint(0, 15, L, dtype=np.int32)
+        ev = events_from_random(cc, p, rv, rp, r2)
+        lo, hi = g["ev_ptr"][i], g["ev_ptr"][i + 1]
+        assert np.array_equal(ev & 0xFFFFFF, g["ev_loc"][lo:hi].astype(np.uint32))
+        assert np.array_equal(ev >> 24, g["ev_outcome"][lo:hi].astype(np.uint32))
+
+
+def test_own_logicals_are_valid():
+    from qldpc_b200.codes.bb_code import make_bb_code
+    c = make_bb_code("[[72, 12, 6]]")
+    Hx, Hz, Lx, Lz = c["Hx"], c["Hz"], c["Lx"], c["Lz"]
+    assert Lx.shape == (12, 72) and Lz.shape == (12, 72)
+    assert not ((Hz @ Lx.T) % 2).any() and not ((Hx @ Lz.T) % 2).any()
+    assert np.array_equal((Lx.astype(int) @ Lz.T.astype(int)) % 2, np.eye(12, dtype=int))
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+import qldpc_b200
+from qldpc_b200.simulation import engine
+rank, world = int(sys.argv[2]), 2
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[3])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+round_total = 11
+lo, hi = engine.shard_range(round_total, rank, world)
+flags = (np.arange(lo, hi) % 3 == 0).astype(np.uint8)
+allf = engine._gather_flags(dist, world, flags, round_total)
+assert np.array_equal(allf, (np.arange(round_total) % 3 == 0).astype(np.uint8)), allf
+c = engine._reduce_counts(dist, np.array([rank + 1, 10, 0, hi - lo, 0, 0, 0, 0], dtype=np.int64))
+assert list(c[:4]) == [3, 20, 0, round_total], c
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_reduction(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
