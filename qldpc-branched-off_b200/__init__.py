@@ -7,3 +7,19 @@ Sub-packages mirror the reference's ``src`` tree (``codes``, ``noise``, ``decodi
 fallback: importing a compute entry point without the built library raises.
 """
 __version__ = "0.1.0"
+
+_SRC_MODULES = ("codes", "codes.bb_code", "noise", "noise.builder", "noise.compiled", "noise.simulation",
+                "decoding", "decoding.sparse", "decoding.dense", "decoding.osd", "decoding.kernels",
+                "simulation", "simulation.engine", "utils", "utils.caching")
+
+
+def install_as_src():
+    """Alias this package as the reference's ``src`` package, so that an unmodified ``main.py`` of the
+    reference (``from src.simulation.engine import run_simulation`` ...) runs on the GPU backend."""
+    import importlib
+    import sys
+    me = sys.modules[__name__]
+    sys.modules["src"] = me
+    for name in _SRC_MODULES:
+        sys.modules["src." + name] = importlib.import_module(__name__ + "." + name)
+    return me

@@ -122,3 +122,28 @@ def test_two_rank_gloo_reduction(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_install_as_src_aliases_reference_module_names():
+    import importlib
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    try:
+        qldpc_b200.install_as_src()
+        eng = importlib.import_module("src.simulation.engine")
+        assert hasattr(eng, "run_simulation")
+        from src.decoding.sparse import performMinSum_Symmetric_Sparse  # noqa: F401
+        from src.decoding.osd import performOSD_enhanced  # noqa: F401
+        from src.noise.builder import build_decoding_matrices  # noqa: F401
+        from src.utils.caching import compute_cache_key, load_matrices, save_matrices  # noqa: F401
+        from src.codes.bb_code import BBCodeCircuit  # noqa: F401
+        import inspect
+        sig = inspect.signature(eng.run_simulation)
+        for kw in ("Hx", "Hz", "Lx", "Lz", "error_rate", "num_trials", "num_cycles", "maxIter", "osd_order", "use_dynamic_alpha",
+                   "alpha_mode", "alvarado_alpha", "precomputed_matrices", "num_workers", "base_seed", "use_jit",
+                   "target_logical_errors", "max_trials", "scopt", "estimation_plot_dir"):
+            assert kw in sig.parameters
+    finally:
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
