@@ -150,28 +150,33 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     for (int j = 0; j < n; ++j) max_cd = std::max(max_cd, colptr[j + 1] - colptr[j]);
     d->max_row_deg = max_rd; d->max_col_deg = max_cd;
     d->fast_ok = (n <= 65534) && (max_rd <= MS_MAX_ROW_DEG) && (m < (1 << 24));
-    // sliced ELL
+    // sliced, chunked ELL (see GraphDev)
     g.n_rslices = g.mw; g.n_cslices = g.nw;
     std::vector<int32_t> rsp(g.n_rslices + 1, 0), csp(g.n_cslices + 1, 0);
     for (int s = 0; s < g.n_rslices; ++s) {
         int deg = 0;
         for (int r = s * 32; r < std::min(m, s * 32 + 32); ++r) deg = std::max(deg, indptr[r + 1] - indptr[r]);
-        rsp[s + 1] = rsp[s] + deg * 32;
+        rsp[s + 1] = rsp[s] + ceil_div(deg, 8) * 32;
     }
     for (int s = 0; s < g.n_cslices; ++s) {
         int deg = 0;
         for (int j = s * 32; j < std::min(n, s * 32 + 32); ++j) deg = std::max(deg, colptr[j + 1] - colptr[j]);
-        csp[s + 1] = csp[s] + deg * 32;
+        csp[s + 1] = csp[s] + ceil_div(deg, 4) * 32;
     }
-    std::vector<uint16_t> row_ell(rsp.back(), 0xFFFFu);
-    std::vector<uint32_t> col_ell(csp.back(), 0xFFFFFFFFu);
+    std::vector<uint16_t> row_ell((size_t)rsp.back() * 8 + 8, 0xFFFFu);
+    std::vector<uint32_t> col_ell((size_t)csp.back() * 4 + 4, 0xFFFFFFFFu);
     if (d->fast_ok) {
         for (int r = 0; r < m; ++r)
-            for (int e = indptr[r]; e < indptr[r + 1]; ++e)
-                row_ell[rsp[r >> 5] + (e - indptr[r]) * 32 + (r & 31)] = (uint16_t)indices[e];
+            for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
+                const int t = e - indptr[r];
+                row_ell[((size_t)rsp[r >> 5] + (t >> 3) * 32 + (r & 31)) * 8 + (t & 7)] = (uint16_t)indices[e];
+            }
         for (int j = 0; j < n; ++j)
-            for (int p = colptr[j]; p < colptr[j + 1]; ++p)
-                col_ell[csp[j >> 5] + (p - colptr[j]) * 32 + (j & 31)] = ((uint32_t)rowidx[p] << 8) | (uint32_t)pos_in_row[csc_edge[p]];
+            for (int p = colptr[j]; p < colptr[j + 1]; ++p) {
+                const int t = p - colptr[j];
+                col_ell[((size_t)csp[j >> 5] + (t >> 2) * 32 + (j & 31)) * 4 + (t & 3)] =
+                    ((uint32_t)rowidx[p] << 8) | (uint32_t)pos_in_row[csc_edge[p]];
+            }
     }
     std::vector<float> pf(n);
     for (int j = 0; j < n; ++j) pf[j] = (float)prior[j];
@@ -184,7 +189,9 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     int rc = QB_OK;
     int32_t *p32; uint16_t *p16; uint32_t *pu32; float *pfl;
 #define UP(vec, ptr, field) if (!rc) { rc = to_device(d->owned, vec, &ptr); field = ptr; }
-    UP(rsp, p32, g.rslice_ptr) UP(row_ell, p16, g.row_ell) UP(csp, p32, g.cslice_ptr) UP(col_ell, pu32, g.col_ell)
+    UP(rsp, p32, g.rslice_ptr) UP(csp, p32, g.cslice_ptr)
+    if (!rc) { rc = to_device(d->owned, row_ell, &p16); g.row_ell4 = reinterpret_cast<const uint4 *>(p16); }
+    if (!rc) { rc = to_device(d->owned, col_ell, &pu32); g.col_ell4 = reinterpret_cast<const uint4 *>(pu32); }
     UP(d->h_indptr, p32, g.indptr) UP(d->h_indices, p32, g.indices) UP(colptr, p32, g.colptr) UP(rowidx, p32, g.rowidx)
     UP(csc_edge, p32, g.csc_edge) UP(logmask, pu32, g.logmask)
     if (!rc) { rc = to_device(d->owned, pf, &pfl); g.prior = pfl; d->d_prior = pfl; }

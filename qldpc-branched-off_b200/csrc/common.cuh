@@ -40,19 +40,21 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int MS_THREADS = 512;      // min-sum CTA size (16 warps)
 constexpr int MS_MAX_ROW_DEG = 57;   // sign bits + argmin + total sign must fit two 32-bit words
-constexpr int OSD_THREADS = 512;
+constexpr int OSD_THREADS = 128;
 constexpr int OSD_MAX_WPL = 4;       // syndrome words per lane -> m <= 4096
 
 // Device view of one decoding side (what kernels receive by value).
 struct GraphDev {
     int m, n, nnz, k, mw, nw, m_pad, n_pad;
     int n_rslices, n_cslices;
-    // sliced ELL, 32 rows / 32 columns per slice, slice s occupies [ptr[s], ptr[s+1]) entries,
-    // entry (t, lane) at ptr[s] + 32*t + lane
+    // sliced, chunked ELL: 32 rows (columns) per slice; slice s owns uint4 words [ptr[s], ptr[s+1]);
+    // word ptr[s] + 32*c + lane holds entries 8c..8c+7 (rows: uint16 column index, 0xFFFF = padding)
+    // resp. 4c..4c+3 (columns: uint32 check << 8 | position in row, 0xFFFFFFFF = padding) of the
+    // lane's row / column, so a warp reads one coalesced 512-byte line per chunk.
     const int32_t *rslice_ptr;
-    const uint16_t *row_ell;    // column index, 0xFFFF = padding
+    const uint4 *row_ell4;
     const int32_t *cslice_ptr;
-    const uint32_t *col_ell;    // check << 8 | position in row, 0xFFFFFFFF = padding
+    const uint4 *col_ell4;
     // plain CSR / CSC (general kernels, OSD)
     const int32_t *indptr, *indices;           // CSR
     const int32_t *colptr, *rowidx, *csc_edge; // CSC: row index and CSR edge id of each entry

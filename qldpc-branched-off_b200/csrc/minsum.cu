@@ -27,6 +27,25 @@ namespace qb {
 
 // ------------------------------------------------------------------------------------------------
 template <int S>
+__device__ __forceinline__ void load_vals(const float *vals, uint32_t j, float (&v)[S])
+{
+    if constexpr (S == 4) {
+        const float4 f = *reinterpret_cast<const float4 *>(vals + j * 4);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else if constexpr (S == 2) {
+        const float2 f = *reinterpret_cast<const float2 *>(vals + j * 2);
+        v[0] = f.x; v[1] = f.y;
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[s] = vals[j * S + s];
+    }
+}
+
+// Check state (uint4 per check and shot):
+//   x = alpha*min1, y = alpha*min2 (float bits)
+//   z = sign of R for row positions 0..31 (already multiplied by the row's total sign)
+//   w = bits 0..24: sign of R for positions 32..56, bits 25..30: argmin position
+template <int S>
 __global__ void __launch_bounds__(MS_THREADS, 1)
 minsum_fast_kernel(GraphDev g, MinsumLaunch a)
 {
@@ -40,7 +59,6 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
     __shared__ int s_nactive;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const float clip = a.clip;
     const int n_tiles = (a.B + S - 1) / S;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -77,82 +95,84 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
 
         for (int it = 0; it < a.max_iter; ++it) {
             const float alpha = a.alpha_d[it];
-            bool act[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) act[s] = s_active[s] != 0;
+            // iteration 0 uses Q = prior unclipped (kernels.py:263-265): old state = 0, clip = inf
+            const float clip = it > 0 ? a.clip : INFINITY;
 
             // ---- phase A: check rows ----------------------------------------------------------
             for (int rs = warp; rs < g.n_rslices; rs += nwarps) {
                 const int base = g.rslice_ptr[rs];
-                const int deg = (g.rslice_ptr[rs + 1] - base) >> 5;
+                const int nch = (g.rslice_ptr[rs + 1] - base) >> 5;
+                if (nch == 0) continue;
+                const uint4 *ell = g.row_ell4 + base + lane;
                 const int r = rs * 32 + lane;
-                float o1[S], o2[S];
-                unsigned long long osg[S];
+                uint32_t o1[S], o2[S], oz[S], ow[S];
                 int oam[S];
-                uint32_t otot[S];
                 float mn1[S], mn2[S];
-                unsigned long long nsg[S];
+                uint32_t nz[S], nw_[S];
                 int am[S];
-                uint32_t npar[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    mn1[s] = INFINITY; mn2[s] = INFINITY; nsg[s] = 0ull; am[s] = 0; npar[s] = 0u;
+                    mn1[s] = INFINITY; mn2[s] = INFINITY; nz[s] = 0u; nw_[s] = 0u; am[s] = 0;
                     if (it > 0) {
-                        uint4 st = chk[s * g.m_pad + r];
-                        o1[s] = __uint_as_float(st.x); o2[s] = __uint_as_float(st.y);
-                        osg[s] = (unsigned long long)st.z | ((unsigned long long)(st.w & 0x01FFFFFFu) << 32);
-                        oam[s] = (st.w >> 25) & 63; otot[s] = st.w >> 31;
+                        const uint4 st = chk[s * g.m_pad + r];
+                        o1[s] = st.x; o2[s] = st.y; oz[s] = st.z; ow[s] = st.w; oam[s] = (int)(st.w >> 25);
                     } else {
-                        o1[s] = 0.f; o2[s] = 0.f; osg[s] = 0ull; oam[s] = -1; otot[s] = 0u;
+                        o1[s] = 0u; o2[s] = 0u; oz[s] = 0u; ow[s] = 0u; oam[s] = -1;
                     }
                 }
-                for (int t = 0; t < deg; ++t) {
-                    const uint32_t j = g.row_ell[base + t * 32 + lane];
-                    if (j != 0xFFFFu) {
-                        float v[S];
-                        if constexpr (S == 4) {
-                            float4 f = *reinterpret_cast<const float4 *>(vals + j * 4);
-                            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-                        } else if constexpr (S == 2) {
-                            float2 f = *reinterpret_cast<const float2 *>(vals + j * 2);
-                            v[0] = f.x; v[1] = f.y;
-                        } else {
+                uint4 cur = ell[0];
+                for (int c = 0; c < nch; ++c) {
+                    const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];         // prefetch next chunk
+                    const uint32_t idx[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
+                                             cur.z & 0xFFFFu, cur.z >> 16, cur.w & 0xFFFFu, cur.w >> 16};
+                    uint32_t owc[S], nsc[S];
+                    int dlt[S];
+                    const int sh = (c & 3) * 8;
 #pragma unroll
-                            for (int s = 0; s < S; ++s) v[s] = vals[j * S + s];
-                        }
+                    for (int s = 0; s < S; ++s) {
+                        owc[s] = (c < 4 ? oz[s] : ow[s]) >> sh;
+                        dlt[s] = oam[s] - c * 8;
+                        nsc[s] = 0u;
+                    }
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            if (!act[s]) continue;
-                            float q = v[s];
-                            if (it > 0) {
-                                float omag = (t == oam[s]) ? o2[s] : o1[s];
-                                uint32_t osgn = ((uint32_t)(osg[s] >> t) & 1u) ^ otot[s];
-                                float rold = osgn ? -omag : omag;
-                                q = v[s] - rold;
-                                if (q != q) q = 0.f;                 // kernels.py:328-329
-                                else q = fminf(fmaxf(q, -clip), clip);
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t j = idx[i];
+                        if (j != 0xFFFFu) {
+                            float v[S];
+                            load_vals<S>(vals, j, v);
+                            const int t = c * 8 + i;
+#pragma unroll
+                            for (int s = 0; s < S; ++s) {
+                                const uint32_t omag = (dlt[s] == i) ? o2[s] : o1[s];
+                                const float rold = __uint_as_float(omag ^ ((owc[s] << (31 - i)) & 0x80000000u));
+                                float q = v[s] - rold;
+                                q = (q != q) ? 0.f : q;                            // kernels.py:328-329
+                                q = fminf(fmaxf(q, -clip), clip);
+                                nsc[s] |= (__float_as_uint(q) >> (31 - i)) & (1u << i);   // val >= 0 -> '+', kernels.py:296
+                                const float ab = fabsf(q);
+                                am[s] = (ab < mn1[s]) ? t : am[s];                 // strict <: first minimum wins
+                                mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
+                                mn1[s] = fminf(mn1[s], ab);
                             }
-                            const uint32_t neg = (q < 0.f) ? 1u : 0u;   // val >= 0 -> '+', kernels.py:296
-                            nsg[s] |= (unsigned long long)neg << t;
-                            npar[s] ^= neg;
-                            const float ab = fabsf(q);
-                            am[s] = (ab < mn1[s]) ? t : am[s];         // strict <: first minimum wins
-                            mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
-                            mn1[s] = fminf(mn1[s], ab);
                         }
                     }
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (c < 4) nz[s] |= nsc[s] << sh; else nw_[s] |= nsc[s] << sh;
+                    }
+                    cur = nxt;
                 }
                 if (r < g.m) {
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        if (!act[s]) continue;
-                        uint32_t sbit = (syn[s * g.mw + (r >> 5)] >> (r & 31)) & 1u;
-                        uint32_t tot = sbit ^ npar[s];
+                        const uint32_t sbit = (syn[s * g.mw + (r >> 5)] >> (r & 31)) & 1u;
+                        const uint32_t tot = (sbit ^ (uint32_t)(__popc(nz[s]) + __popc(nw_[s]))) & 1u;
+                        const uint32_t tmask = 0u - tot;
                         uint4 st;
                         st.x = __float_as_uint(alpha * mn1[s]);
                         st.y = __float_as_uint(alpha * mn2[s]);
-                        st.z = (uint32_t)nsg[s];
-                        st.w = ((uint32_t)(nsg[s] >> 32) & 0x01FFFFFFu) | ((uint32_t)am[s] << 25) | (tot << 31);
+                        st.z = nz[s] ^ tmask;
+                        st.w = ((nw_[s] ^ tmask) & 0x01FFFFFFu) | ((uint32_t)am[s] << 25);
                         chk[s * g.m_pad + r] = st;
                     }
                 }
@@ -162,44 +182,58 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             // ---- phase B: variables ------------------------------------------------------------
             for (int cs = warp; cs < g.n_cslices; cs += nwarps) {
                 const int base = g.cslice_ptr[cs];
-                const int deg = (g.cslice_ptr[cs + 1] - base) >> 5;
+                const int nch = (g.cslice_ptr[cs + 1] - base) >> 5;
+                const uint4 *ell = g.col_ell4 + base + lane;
                 const int j = cs * 32 + lane;
                 float acc[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) acc[s] = 0.f;
-                for (int t = 0; t < deg; ++t) {
-                    const uint32_t e = g.col_ell[base + t * 32 + lane];
-                    if (e != 0xFFFFFFFFu) {
-                        const int c = e >> 8, pos = e & 255;
+                uint4 e4 = nch ? ell[0] : make_uint4(~0u, ~0u, ~0u, ~0u);
+                for (int c = 0; c < nch; ++c) {
+                    const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];
+                    const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            if (!act[s]) continue;
-                            const uint4 st = chk[s * g.m_pad + c];
-                            const float mag = (pos == (int)((st.w >> 25) & 63)) ? __uint_as_float(st.y) : __uint_as_float(st.x);
-                            const uint32_t word = pos < 32 ? st.z : st.w;
-                            const uint32_t sgn = ((word >> (pos & 31)) & 1u) ^ (st.w >> 31);
-                            acc[s] += sgn ? -mag : mag;            // R_sum[col] += msg, kernels.py:316
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t e = ent[i];
+                        if (e != 0xFFFFFFFFu) {
+                            const uint32_t cidx = e >> 8, pos = e & 63u;
+                            const bool hi = pos >= 32u;
+                            const uint32_t shl = 31u - (pos & 31u);
+#pragma unroll
+                            for (int s = 0; s < S; ++s) {
+                                const uint4 st = chk[s * g.m_pad + cidx];
+                                const uint32_t mag = ((st.w >> 25) == pos) ? st.y : st.x;
+                                const uint32_t word = hi ? st.w : st.z;
+                                acc[s] += __uint_as_float(mag ^ ((word << shl) & 0x80000000u));   // R_sum[col] += msg, kernels.py:316
+                            }
                         }
                     }
+                    e4 = nxt;
                 }
                 if (j < g.n) {
                     const float pr = g.prior[j];
                     uint32_t negmask = 0u;
+                    float v[S];
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        if (!act[s]) continue;
-                        const float v = acc[s] + pr;               // kernels.py:320
-                        vals[j * S + s] = v;
-                        if (v < 0.f) negmask |= 1u << s;           // kernels.py:349
+                        v[s] = acc[s] + pr;                        // kernels.py:320
+                        if (v[s] < 0.f) negmask |= 1u << s;        // kernels.py:349
                     }
+                    if constexpr (S == 4) *reinterpret_cast<float4 *>(vals + j * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                    else if constexpr (S == 2) *reinterpret_cast<float2 *>(vals + j * 2) = make_float2(v[0], v[1]);
+                    else vals[j] = v[0];
                     if (negmask) {
-                        for (int t = 0; t < deg; ++t) {
-                            const uint32_t e = g.col_ell[base + t * 32 + lane];
-                            if (e == 0xFFFFFFFFu) break;
-                            const int c = e >> 8;
+                        for (int c = 0; c < nch; ++c) {
+                            const uint4 q4 = ell[c * 32];
+                            const uint32_t ent[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                            for (int s = 0; s < S; ++s)
-                                if (negmask & (1u << s)) atomicXor(&par[s * g.mw + (c >> 5)], 1u << (c & 31));
+                            for (int i = 0; i < 4; ++i) {
+                                if (ent[i] == 0xFFFFFFFFu) continue;
+                                const uint32_t cidx = ent[i] >> 8;
+#pragma unroll
+                                for (int s = 0; s < S; ++s)
+                                    if (negmask & (1u << s)) atomicXor(&par[s * g.mw + (cidx >> 5)], 1u << (cidx & 31));
+                            }
                         }
                     }
                 }
@@ -213,11 +247,13 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             }
             __syncthreads();
             const bool last = (it == a.max_iter - 1);
+            bool any_done = false;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                if (!act[s]) continue;
+                if (!s_active[s]) continue;
                 const bool conv = (s_unsat[s] == 0);
                 if (conv || last) {
+                    any_done = true;
                     const size_t shot = shot0 + s;
                     for (int j = tid; j < g.n_pad; j += blockDim.x) {
                         const float v = vals[j * S + s];
@@ -232,18 +268,22 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                     }
                 }
             }
-            __syncthreads();
-            if (tid == 0) {
-                int na = 0;
-                for (int s = 0; s < S; ++s) {
-                    if (s_active[s] && (s_unsat[s] == 0 || last)) s_active[s] = 0;
-                    s_unsat[s] = 0;
-                    na += s_active[s];
+            if (any_done || last) {                       // uniform across the CTA
+                __syncthreads();
+                if (tid == 0) {
+                    int na = 0;
+                    for (int s = 0; s < S; ++s) {
+                        if (s_active[s] && (s_unsat[s] == 0 || last)) s_active[s] = 0;
+                        na += s_active[s];
+                    }
+                    s_nactive = na;
                 }
-                s_nactive = na;
             }
             __syncthreads();
+            if (tid < S) s_unsat[tid] = 0;
             if (s_nactive == 0) break;
+            // a finished shot keeps being iterated (its outputs are already written and never
+            // overwritten: s_active gates the output stage), which keeps the inner loops branch-free.
         }
         __syncthreads();
     }

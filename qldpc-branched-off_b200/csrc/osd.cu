@@ -26,26 +26,96 @@
 
 namespace qb {
 
+constexpr int OSD_NW = OSD_THREADS / 32;   // warps per CTA = candidates reduced per round
+constexpr int SEL_BINS = 2048;             // histogram bins: float bits 30..20 (8 bins per octave)
+constexpr int SEL_SHIFT = 20;
+constexpr int SEL_CAP = 2048;              // candidates materialised per selection window
+constexpr int SEL_MIN = 512;               // a window is closed once it holds at least this many
+
 struct OsdArgs {
     GraphDev g;
     OsdLaunch a;
-    int sort_in_smem;     // keys / index ping-pong buffers in shared memory
     int tcap;             // T columns resident in shared memory; the rest spills to gT
-    uint32_t *gT;         // [grid][(min(m,n) - tcap) * mw] spill
-    uint32_t *gkeys;      // [grid][n] when !sort_in_smem
-    uint16_t *gidx;       // [grid][2][n_pad] when !sort_in_smem
+    int cstride;          // words per T column (mw + 1 when mw is even: conflict-free column-parallel reads)
     int rank_cap;         // min(m, n)
+    uint32_t *gT;         // [grid][(rank_cap - tcap) * cstride] spill
+    // per-CTA global scratch for the rare paths: later selection windows and the full-sort fallback
+    uint32_t *g_hist;     // [grid][SEL_BINS]
+    uint16_t *g_off;      // [grid][SEL_BINS + 1]
+    uint32_t *g_listK;    // [grid][SEL_CAP]
+    uint16_t *g_listI;    // [grid][SEL_CAP]
+    uint32_t *g_keys;     // [grid][n]          (full sort)
+    uint16_t *g_idx;      // [grid][2][n_pad2]  (full sort)
+    uint32_t *g_cnt;      // [grid][256 * OSD_NW]
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
 
+// Stable LSD radix sort (4 x 8 bit) of idx[] by keys[idx]; warps own contiguous segments so the
+// (digit, warp) counter order is the element order.  Result ends in idx0.  Fallback path only.
+__device__ void full_radix_sort(const uint32_t *keys, uint16_t *idx0, uint16_t *idx1, uint32_t *cnt, int n)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    __shared__ uint32_t wsum[32];
+    const int seg = ((n + NW - 1) / NW + 31) & ~31;
+    const int s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
+    uint16_t *src = idx0, *dst = idx1;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * 8;
+        for (int i = tid; i < 256 * NW; i += blockDim.x) cnt[i] = 0u;
+        __syncthreads();
+        for (int i0 = s0; i0 < s1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < s1;
+            const uint32_t d = valid ? ((keys[src[i]] >> shift) & 255u) : (256u + lane);
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+            if (valid && (peers & lanemask_lt()) == 0) cnt[d * NW + warp] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            const int total = 256 * NW, per = (total + blockDim.x - 1) / blockDim.x;
+            const int b0 = tid * per;
+            uint32_t local = 0;
+            for (int i = b0; i < min(total, b0 + per); ++i) local += cnt[i];
+            uint32_t inc = local;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t x = lane < NW ? wsum[lane] : 0u, xi = x;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, o); if (lane >= o) xi += y; }
+                wsum[lane] = xi - x;
+            }
+            __syncthreads();
+            uint32_t run = wsum[warp] + inc - local;
+            for (int i = b0; i < min(total, b0 + per); ++i) { const uint32_t c = cnt[i]; cnt[i] = run; run += c; }
+        }
+        __syncthreads();
+        for (int i0 = s0; i0 < s1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < s1;
+            const uint16_t id = valid ? src[i] : (uint16_t)0;
+            const uint32_t d = valid ? ((keys[id] >> shift) & 255u) : (256u + lane);
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+            if (valid) dst[cnt[d * NW + warp] + __popc(peers & lanemask_lt())] = id;
+            __syncwarp();
+            if (valid && (peers & lanemask_lt()) == 0) cnt[d * NW + warp] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        uint16_t *tmp = src; src = dst; dst = tmp;
+    }
+}
+
 template <int WPL>
-__global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
+__global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
 {
     const GraphDev &g = P.g;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-    const int mw = g.mw, n = g.n, m = g.m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = OSD_NW;
+    const int mw = g.mw, n = g.n, m = g.m, cs = P.cstride;
     const int n_pad2 = (n + 1) & ~1;
 
     // ---- shared memory carve-up -------------------------------------------------------------------
@@ -54,30 +124,22 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
     uint16_t *row_at_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
     int16_t *pivcol_of_row = reinterpret_cast<int16_t *>(sp); sp += sizeof(int16_t) * g.m_pad;
     uint16_t *piv_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
-    int32_t *piv_cand = reinterpret_cast<int32_t *>(sp); sp += sizeof(int32_t) * g.m_pad;
+    uint16_t *piv_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // position in the ordering
+    uint16_t *piv_col = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // column index
     uint32_t *npmask = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
     uint32_t *sv = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
     uint32_t *pv = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
-    int *flags = reinterpret_cast<int *>(sp); sp += sizeof(int) * 32;
-    uint16_t *idx0 = nullptr, *idx1 = nullptr;
-    uint32_t *keys = nullptr, *cnt = nullptr;
-    unsigned char *regionX;
-    if (P.sort_in_smem) {
-        idx0 = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * n_pad2;
-        regionX = sp;                       // sort scratch, later overlaid by T
-        keys = reinterpret_cast<uint32_t *>(regionX);
-        idx1 = reinterpret_cast<uint16_t *>(regionX + sizeof(uint32_t) * n);
-        cnt = reinterpret_cast<uint32_t *>(regionX + sizeof(uint32_t) * n + sizeof(uint16_t) * n_pad2);
-    } else {
-        regionX = sp;
-        cnt = reinterpret_cast<uint32_t *>(regionX);     // 256*NW counters, overlaid by T afterwards
-        keys = P.gkeys + (size_t)blockIdx.x * n;
-        idx0 = P.gidx + (size_t)blockIdx.x * 2 * n_pad2;
-        idx1 = idx0 + n_pad2;
-    }
-    uint32_t *Tsm = reinterpret_cast<uint32_t *>(regionX);
-    uint32_t *Tgl = P.gT ? P.gT + (size_t)blockIdx.x * (size_t)(P.rank_cap - P.tcap) * mw : nullptr;
-    __shared__ int s_rho;
+    uint16_t *ord = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * SEL_CAP;   // current window, sorted
+    uint32_t *regionX = reinterpret_cast<uint32_t *>(sp);
+    // selection scratch of the first window overlays T (T is empty until the first pivot)
+    uint32_t *s_hist = regionX;
+    uint16_t *s_off = reinterpret_cast<uint16_t *>(s_hist + SEL_BINS);
+    uint32_t *s_listK = reinterpret_cast<uint32_t *>(s_off + SEL_BINS + 2);
+    uint16_t *s_listI = reinterpret_cast<uint16_t *>(s_listK + SEL_CAP);
+    uint32_t *Tsm = regionX;
+    uint32_t *Tgl = P.gT ? P.gT + (size_t)blockIdx.x * (size_t)(P.rank_cap - P.tcap) * cs : nullptr;
+    __shared__ int s_flags[NW];
+    __shared__ int s_rho, s_binhi, s_wincount;
 
     const int F = P.a.n_fail_d ? min(*P.a.n_fail_d, P.a.F) : P.a.F;
 
@@ -85,6 +147,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
         const int shot = P.a.fail_idx ? P.a.fail_idx[qi] : qi;
         const uint32_t *hard = P.a.hard_bits + (size_t)shot * g.nw;
         const int32_t *ext_order = P.a.ordering ? P.a.ordering + (size_t)shot * n : nullptr;
+        const float *post = P.a.post ? P.a.post + (size_t)shot * n : nullptr;
 
         // ---- 1. residual syndrome, bookkeeping ----------------------------------------------------
         for (int w = tid; w < 32 * WPL; w += blockDim.x) {
@@ -95,6 +158,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
             npmask[w] = full;
         }
         for (int r = tid; r < g.m_pad; r += blockDim.x) { pos_of_row[r] = (uint16_t)r; row_at_pos[r] = (uint16_t)r; pivcol_of_row[r] = -1; }
+        if (!ext_order) for (int b = tid; b < SEL_BINS; b += blockDim.x) s_hist[b] = 0u;
         __syncthreads();
         for (int w = tid; w < g.nw; w += blockDim.x) {
             uint32_t bits = hard[w];
@@ -105,86 +169,126 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
                     for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) { const int r = g.rowidx[p]; atomicXor(&sv[r >> 5], 1u << (r & 31)); }
             }
         }
-
-        // ---- 2. stable sort of columns by |posterior| -----------------------------------------------
-        if (!ext_order) {
-            const float *post = P.a.post + (size_t)shot * n;
-            for (int j = tid; j < n; j += blockDim.x) { keys[j] = __float_as_uint(fabsf(post[j])); idx0[j] = (uint16_t)j; }
-            const int seg = ((n + NW - 1) / NW + 31) & ~31;
-            const int s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
-            uint16_t *src = idx0, *dst = idx1;
-            for (int pass = 0; pass < 4; ++pass) {
-                const int shift = pass * 8;
-                for (int i = tid; i < 256 * NW; i += blockDim.x) cnt[i] = 0u;
-                __syncthreads();
-                for (int i0 = s0; i0 < s1; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool valid = i < s1;
-                    const uint32_t d = valid ? ((keys[src[i]] >> shift) & 255u) : (256u + lane);
-                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-                    if (valid && (peers & lanemask_lt()) == 0) cnt[d * NW + warp] += __popc(peers);
-                    __syncwarp();
-                }
-                __syncthreads();
-                {   // exclusive scan of cnt[256*NW] in (digit, warp) order
-                    const int total = 256 * NW, per = (total + blockDim.x - 1) / blockDim.x;
-                    const int b0 = tid * per;
-                    uint32_t local = 0;
-                    for (int i = b0; i < min(total, b0 + per); ++i) local += cnt[i];
-                    uint32_t inc = local;
-                    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
-                    __shared__ uint32_t wsum[32];
-                    if (lane == 31) wsum[warp] = inc;
-                    __syncthreads();
-                    if (warp == 0) {
-                        uint32_t x = lane < NW ? wsum[lane] : 0u, xi = x;
-                        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, xi, o); if (lane >= o) xi += y; }
-                        wsum[lane] = xi - x;
-                    }
-                    __syncthreads();
-                    uint32_t run = wsum[warp] + inc - local;
-                    for (int i = b0; i < min(total, b0 + per); ++i) { const uint32_t c = cnt[i]; cnt[i] = run; run += c; }
-                }
-                __syncthreads();
-                for (int i0 = s0; i0 < s1; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool valid = i < s1;
-                    const uint16_t id = valid ? src[i] : (uint16_t)0;
-                    const uint32_t d = valid ? ((keys[id] >> shift) & 255u) : (256u + lane);
-                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-                    if (valid) {
-                        const uint32_t base = cnt[d * NW + warp];
-                        dst[base + __popc(peers & lanemask_lt())] = id;
-                    }
-                    __syncwarp();
-                    if (valid && (peers & lanemask_lt()) == 0) cnt[d * NW + warp] += __popc(peers);
-                    __syncwarp();
-                }
-                __syncthreads();
-                uint16_t *tmp = src; src = dst; dst = tmp;
-            }
-            // after 4 passes the result is back in idx0
-        }
+        // ---- 2a. histogram of |posterior| bit patterns (selection pass 1) ---------------------------
+        if (!ext_order)
+            for (int j = tid; j < n; j += blockDim.x) atomicAdd(&s_hist[__float_as_uint(fabsf(post[j])) >> SEL_SHIFT], 1u);
         __syncthreads();
 
-        // ---- 3. elimination ---------------------------------------------------------------------------
-        auto order_at = [&](int c) -> int { return ext_order ? ext_order[c] : (int)idx0[c]; };
-        auto Tcol = [&](int x) -> uint32_t * { return x < P.tcap ? Tsm + (size_t)x * mw : Tgl + (size_t)(x - P.tcap) * mw; };
+        // ordering modes: 0 = caller-supplied, 1 = selection windows, 2 = full sort in global scratch
+        int mode = ext_order ? 0 : 1;
+        int bin_next = 0;                 // first histogram bin not yet consumed
+        int win_start = 0, win_end = ext_order ? n : 0;
+        uint32_t *hist = s_hist; uint16_t *off = s_off; uint32_t *listK = s_listK; uint16_t *listI = s_listI;
+        const uint16_t *gsorted = nullptr;
+
+        auto Tcol = [&](int x) -> uint32_t * { return x < P.tcap ? Tsm + (size_t)x * cs : Tgl + (size_t)(x - P.tcap) * cs; };
+        auto order_at = [&](int c) -> int {
+            if (mode == 0) return ext_order[c];
+            if (mode == 2) return (int)gsorted[c];
+            return (int)ord[c - win_start];
+        };
         auto unresolved = [&]() -> bool {
             bool any = false;
 #pragma unroll
             for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; any |= (sv[w] & npmask[w]) != 0u; }
             return __any_sync(0xFFFFFFFFu, any);
         };
+
         int t = 0;
         bool done = !unresolved();
-        for (int c0 = 0; c0 < n && !done && t < P.rank_cap; c0 += NW) {
+        int c0 = 0;
+        while (!done && c0 < n && t < P.rank_cap) {
+            // ---- 2b. materialise the next window of candidates, sorted by (|posterior|, index) --------
+            if (c0 >= win_end && mode == 1) {
+                if (t > 0) {       // T now lives in regionX: later windows use the global scratch
+                    hist = P.g_hist + (size_t)blockIdx.x * SEL_BINS; off = P.g_off + (size_t)blockIdx.x * (SEL_BINS + 2);
+                    listK = P.g_listK + (size_t)blockIdx.x * SEL_CAP; listI = P.g_listI + (size_t)blockIdx.x * SEL_CAP;
+                    for (int b = tid; b < SEL_BINS; b += blockDim.x) hist[b] = 0u;
+                    __syncthreads();
+                    for (int j = tid; j < n; j += blockDim.x) {
+                        const int b = __float_as_uint(fabsf(post[j])) >> SEL_SHIFT;
+                        if (b >= bin_next) atomicAdd(&hist[b], 1u);
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {   // choose [bin_next, bin_hi]: close the window at >= SEL_MIN, never exceed SEL_CAP
+                    int cum = 0, hi = bin_next - 1;
+                    bool stop = false;
+                    for (int b0 = bin_next; b0 < SEL_BINS && !stop; b0 += 32) {
+                        const int b = b0 + lane;
+                        const int cnt = b < SEL_BINS ? (int)hist[b] : 0;
+                        int inc = cnt;
+                        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+                        if (b < SEL_BINS) off[b] = (uint16_t)min(cum + inc - cnt, 65535);
+                        const uint32_t over = __ballot_sync(0xFFFFFFFFu, cum + inc > SEL_CAP);
+                        const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum + inc >= SEL_MIN);
+                        int last = 31;
+                        if (over | enough) {
+                            const int fo = over ? __ffs(over) - 1 : 32, fe = enough ? __ffs(enough) - 1 : 32;
+                            last = fe < fo ? fe : fo - 1;          // stop before a bin that would overflow the window
+                            stop = true;
+                        }
+                        if (last >= 0) { cum += __shfl_sync(0xFFFFFFFFu, inc, last) - 0; hi = b0 + last; }
+                    }
+                    if (!stop) hi = SEL_BINS - 1;
+                    if (lane == 0) { s_binhi = hi; s_wincount = cum; }
+                }
+                __syncthreads();
+                const int bin_hi = s_binhi, M = s_wincount;
+                __syncthreads();
+                if (M == 0) {
+                    if (bin_hi >= SEL_BINS - 1) break;                 // no candidates left
+                    mode = 2;                                          // a single bin exceeds SEL_CAP: full sort
+                } else {
+                    // scatter (unordered inside a bin), then rank inside each bin by (key, index)
+                    for (int j = tid; j < n; j += blockDim.x) {
+                        const uint32_t key = __float_as_uint(fabsf(post[j]));
+                        const int b = key >> SEL_SHIFT;
+                        if (b >= bin_next && b <= bin_hi) {
+                            const uint32_t left = atomicSub(&hist[b], 1u);      // count down: consumed bins end at 0
+                            const int slot = off[b] + (int)left - 1;
+                            listK[slot] = key; listI[slot] = (uint16_t)j;
+                        }
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < M; i += blockDim.x) {
+                        const uint32_t key = listK[i];
+                        const uint16_t id = listI[i];
+                        const int b = key >> SEL_SHIFT;
+                        const int lo = off[b];
+                        int hi2 = M;
+                        if (b < bin_hi) { int bb = b + 1; hi2 = off[bb]; }   // off[] is non-decreasing over the window
+                        int rank = lo;
+                        for (int k2 = lo; k2 < hi2; ++k2) {
+                            const uint32_t kk = listK[k2];
+                            rank += (kk < key) || (kk == key && listI[k2] < id);
+                        }
+                        ord[rank] = id;
+                    }
+                    win_start = win_end; win_end += M; bin_next = bin_hi + 1;
+                    __syncthreads();
+                }
+            }
+            if (mode == 2 && gsorted == nullptr) {
+                uint32_t *keys = P.g_keys + (size_t)blockIdx.x * n;
+                uint16_t *idx0 = P.g_idx + (size_t)blockIdx.x * 2 * n_pad2, *idx1 = idx0 + n_pad2;
+                for (int j = tid; j < n; j += blockDim.x) { keys[j] = __float_as_uint(fabsf(post[j])); idx0[j] = (uint16_t)j; }
+                __syncthreads();
+                full_radix_sort(keys, idx0, idx1, P.g_cnt + (size_t)blockIdx.x * 256 * NW, n);
+                gsorted = idx0; win_start = 0; win_end = n;
+                __syncthreads();
+            }
+
+            // ---- 3. reduce NW candidates against the current T -----------------------------------------
             const int c = c0 + warp;
+            const bool have = c < win_end && c < n;
             uint32_t v[WPL];
 #pragma unroll
             for (int i = 0; i < WPL; ++i) v[i] = 0u;
-            if (c < n) {
+            int myj = 0;
+            if (have) {
                 const int j = order_at(c);
+                myj = j;
                 for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) {
                     const int r = g.rowidx[p];
                     const int pc = pivcol_of_row[r];
@@ -203,9 +307,9 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
 #pragma unroll
                 for (int i = 0; i < WPL; ++i) f_ |= (v[i] & npmask[lane + 32 * i]) != 0u;
                 const bool flag = __any_sync(0xFFFFFFFFu, f_);
-                if (lane == 0) flags[warp] = flag ? 1 : 0;
+                if (lane == 0) s_flags[warp] = flag ? 1 : 0;
                 __syncthreads();
-                const uint32_t fb = __ballot_sync(0xFFFFFFFFu, lane < NW && flags[lane] != 0);
+                const uint32_t fb = __ballot_sync(0xFFFFFFFFu, lane < NW && s_flags[lane] != 0);
                 if (fb == 0u) break;
                 const int f = __ffs(fb) - 1;
                 if (warp == f) {
@@ -238,7 +342,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
                         row_at_pos[t] = (uint16_t)rho; row_at_pos[q] = (uint16_t)rt;
                         pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
                         pivcol_of_row[rho] = (int16_t)t;
-                        piv_row[t] = (uint16_t)rho; piv_cand[t] = c;
+                        piv_row[t] = (uint16_t)rho; piv_pos[t] = (uint16_t)c; piv_col[t] = (uint16_t)myj;
                         npmask[rho >> 5] &= ~(1u << (rho & 31));
                         s_rho = rho;
                     }
@@ -258,26 +362,28 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
                     uint32_t mine = 0u;
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) if (i == ri) mine = v[i];
-                    const uint32_t has = __shfl_sync(0xFFFFFFFFu, mine, rl) & rbit;
-                    if (has) {
+                    if (__shfl_sync(0xFFFFFFFFu, mine, rl) & rbit) {
 #pragma unroll
                         for (int i = 0; i < WPL; ++i) v[i] ^= u[i];
                     }
                 }
-                // (b) stored columns of earlier pivots and (c) the transformed syndrome (slot t)
-                for (int x = warp; x <= t; x += NW) {
-                    uint32_t *col = (x == t) ? sv : Tcol(x);
-                    uint32_t cw[WPL];
+                // (b) stored columns of earlier pivots: 32 columns are tested per shared-memory read
+                for (int x0 = warp * 32; x0 < t; x0 += NW * 32) {
+                    const int x = x0 + lane;
+                    const bool has = x < t && (Tcol(x)[rw] & rbit) != 0u;
+                    uint32_t msk = __ballot_sync(0xFFFFFFFFu, has);
+                    while (msk) {
+                        const int b = __ffs(msk) - 1; msk &= msk - 1;
+                        uint32_t *col = Tcol(x0 + b);
 #pragma unroll
-                    for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; cw[i] = (w < mw) ? col[w] : 0u; }
-                    uint32_t mine = 0u;
-#pragma unroll
-                    for (int i = 0; i < WPL; ++i) if (i == ri) mine = cw[i];
-                    const uint32_t has = __shfl_sync(0xFFFFFFFFu, mine, rl) & rbit;
-                    if (has) {
-#pragma unroll
-                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) col[w] = cw[i] ^ u[i]; }
+                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) col[w] ^= u[i]; }
                     }
+                }
+                // (c) the transformed syndrome
+                if (warp == NW - 1 && (sv[rw] & rbit)) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) sv[w] ^= u[i]; }
                 }
                 ++t;
                 __syncthreads();
@@ -285,6 +391,8 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
                 if (done || t >= P.rank_cap) break;
             }
             __syncthreads();
+            c0 += NW;
+            if (mode == 1 && c0 > win_end) c0 = win_end;   // do not skip candidates of the next window
         }
 
         // ---- 5. solution = hard ^ e, e[ordering[pivot_col]] = s_reduced[pivot_row] ---------------
@@ -292,13 +400,13 @@ __global__ void __launch_bounds__(OSD_THREADS, 2) osd0_kernel(OsdArgs P)
         for (int i = tid; i < t; i += blockDim.x) {
             const int rho = piv_row[i];
             if ((sv[rho >> 5] >> (rho & 31)) & 1u) {
-                const int j = order_at(piv_cand[i]);
+                const int j = (int)piv_col[i];
                 atomicXor(&hard_rw[j >> 5], 1u << (j & 31));
             }
         }
         if (P.a.pivots_out)
             for (int i = tid; i < P.rank_cap; i += blockDim.x)
-                P.a.pivots_out[(size_t)shot * P.rank_cap + i] = i < t ? piv_cand[i] : -1;
+                P.a.pivots_out[(size_t)shot * P.rank_cap + i] = i < t ? (int)piv_pos[i] : -1;
         if (P.a.rank_out && tid == 0) P.a.rank_out[shot] = t;
         __syncthreads();
     }
@@ -311,41 +419,38 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     OsdArgs P{};
     P.g = g; P.a = a;
     P.rank_cap = std::min(g.m, g.n);
-    const int NW = OSD_THREADS / 32;
+    P.cstride = (g.mw & 1) ? g.mw : g.mw + 1;
     const int n_pad2 = (g.n + 1) & ~1;
-    const size_t fixed = sizeof(uint16_t) * 4 * (size_t)g.m_pad + sizeof(int32_t) * (size_t)g.m_pad +
-                         sizeof(uint32_t) * 32 * WPL * 3 + sizeof(int) * 32 + 64;
-    const size_t budget = (size_t)dec->max_smem_optin - 2048;   // static __shared__ + slack
-    const size_t sort_x = sizeof(uint32_t) * (size_t)g.n + sizeof(uint16_t) * n_pad2 + sizeof(uint32_t) * 256 * NW;
-    const size_t idx0_b = sizeof(uint16_t) * (size_t)n_pad2;
-    size_t regionX, smem;
-    const size_t colb = sizeof(uint32_t) * (size_t)g.mw;
-    const size_t want = colb * (size_t)P.rank_cap;      // T with every possible pivot resident
-    if (fixed + idx0_b + sort_x <= budget) {
-        P.sort_in_smem = 1;
-        const size_t avail1 = budget - fixed - idx0_b;                                   // 1 CTA / SM
-        const size_t avail2 = budget / 2 > fixed + idx0_b ? budget / 2 - fixed - idx0_b : 0;   // 2 CTAs / SM
-        regionX = std::max(sort_x, std::min(want, sort_x <= avail2 ? avail2 : avail1));
-        smem = fixed + idx0_b + regionX;
-    } else {
-        P.sort_in_smem = 0;
-        const size_t cnt_b = sizeof(uint32_t) * 256 * NW;
-        regionX = std::max(cnt_b, std::min(want, (size_t)96 * 1024));
-        smem = fixed + regionX;
-    }
-    QB_REQUIRE(smem <= budget + 2048, "OSD: problem too large for shared memory");
+    const size_t fixed = sizeof(uint16_t) * 6 * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
+    const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint16_t) * (SEL_BINS + 2) + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
+    const size_t budget = (size_t)dec->max_smem_optin - 1024;
+    const size_t colb = sizeof(uint32_t) * (size_t)P.cstride;
+    const size_t want = colb * (size_t)P.rank_cap;
+    // aim for 4 CTAs per SM; T columns beyond the shared-memory share spill to global memory
+    size_t share = budget / 4 > fixed ? budget / 4 - fixed : 0;
+    size_t regionX = std::max(sel_b, std::min(want, share));
+    size_t smem = fixed + regionX;
+    QB_REQUIRE(smem <= budget, "OSD: problem too large for shared memory");
     P.tcap = (int)std::min<size_t>(P.rank_cap, regionX / colb);
-    int grid = std::max(1, std::min(a.F, dec->sm_count * (smem <= budget / 2 ? 2 : 1)));
-    size_t need = 0;
-    const size_t spill = (size_t)(P.rank_cap - P.tcap) * g.mw * sizeof(uint32_t);
-    const size_t gk = P.sort_in_smem ? 0 : sizeof(uint32_t) * (size_t)g.n;
-    const size_t gi = P.sort_in_smem ? 0 : sizeof(uint16_t) * 2 * (size_t)n_pad2;
-    need = (size_t)grid * (spill + gk + gi) + 256;
+    const int ctas_per_sm = std::max(1, std::min(4, (int)(budget / smem)));
+    const int grid = std::max(1, std::min(a.F, dec->sm_count * ctas_per_sm));
+    const size_t spill = (size_t)(P.rank_cap - P.tcap) * P.cstride * sizeof(uint32_t);
+    const size_t b_hist = sizeof(uint32_t) * SEL_BINS, b_off = sizeof(uint16_t) * (SEL_BINS + 2);
+    const size_t b_lk = sizeof(uint32_t) * SEL_CAP, b_li = sizeof(uint16_t) * SEL_CAP;
+    const size_t b_keys = sizeof(uint32_t) * (size_t)g.n, b_idx = sizeof(uint16_t) * 2 * (size_t)n_pad2, b_cnt = sizeof(uint32_t) * 256 * OSD_NW;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t G = (size_t)grid;
+    const size_t need = al(G * spill) + al(G * b_hist) + al(G * b_off) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
     if (int rc = dec->work.ensure(need)) return rc;
-    unsigned char *base = dec->work.as<unsigned char>();
-    P.gT = spill ? reinterpret_cast<uint32_t *>(base) : nullptr;
-    P.gkeys = reinterpret_cast<uint32_t *>(base + (size_t)grid * spill);
-    P.gidx = reinterpret_cast<uint16_t *>(base + (size_t)grid * (spill + gk));
+    unsigned char *p = dec->work.as<unsigned char>();
+    P.gT = spill ? reinterpret_cast<uint32_t *>(p) : nullptr; p += al(G * spill);
+    P.g_hist = reinterpret_cast<uint32_t *>(p); p += al(G * b_hist);
+    P.g_off = reinterpret_cast<uint16_t *>(p); p += al(G * b_off);
+    P.g_listK = reinterpret_cast<uint32_t *>(p); p += al(G * b_lk);
+    P.g_listI = reinterpret_cast<uint16_t *>(p); p += al(G * b_li);
+    P.g_keys = reinterpret_cast<uint32_t *>(p); p += al(G * b_keys);
+    P.g_idx = reinterpret_cast<uint16_t *>(p); p += al(G * b_idx);
+    P.g_cnt = reinterpret_cast<uint32_t *>(p);
     QB_CUDA(cudaFuncSetAttribute(osd0_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     osd0_kernel<WPL><<<grid, OSD_THREADS, smem, st>>>(P);
     QB_CUDA(cudaGetLastError());
@@ -360,6 +465,7 @@ int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
         set_error("OSD-0 kernel supports n <= 65535 columns and m <= 4096 rows");
         return QB_ERR_UNSUPPORTED;
     }
+    if (!a.ordering && !a.post) { set_error("OSD-0 needs posteriors or an ordering"); return QB_ERR_ARG; }
     const int wpl = ceil_div(g.mw, 32);
     switch (wpl) {
         case 1: return launch_osd_wpl<1>(dec, a, st);
