@@ -178,6 +178,12 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
                     ((uint32_t)rowidx[p] << 8) | (uint32_t)pos_in_row[csc_edge[p]];
             }
     }
+    std::vector<uint16_t> colsig;
+    if (max_cd <= 8 && m <= 65534) {
+        colsig.assign((size_t)std::max(1, n) * 8, 0xFFFFu);
+        for (int j = 0; j < n; ++j)
+            for (int p = colptr[j]; p < colptr[j + 1]; ++p) colsig[(size_t)j * 8 + (p - colptr[j])] = (uint16_t)rowidx[p];
+    }
     std::vector<float> pf(n);
     for (int j = 0; j < n; ++j) pf[j] = (float)prior[j];
     std::vector<uint32_t> logmask(n, 0u);
@@ -195,6 +201,8 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     UP(d->h_indptr, p32, g.indptr) UP(d->h_indices, p32, g.indices) UP(colptr, p32, g.colptr) UP(rowidx, p32, g.rowidx)
     UP(csc_edge, p32, g.csc_edge) UP(logmask, pu32, g.logmask)
     if (!rc) { rc = to_device(d->owned, pf, &pfl); g.prior = pfl; d->d_prior = pfl; }
+    g.colsig = nullptr;
+    if (!rc && !colsig.empty()) { rc = to_device(d->owned, colsig, &p16); g.colsig = reinterpret_cast<const uint4 *>(p16); }
 #undef UP
     if (rc) { qb_decoder_destroy(d); return rc; }
     *out = d;

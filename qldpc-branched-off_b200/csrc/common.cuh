@@ -58,6 +58,7 @@ struct GraphDev {
     // plain CSR / CSC (general kernels, OSD)
     const int32_t *indptr, *indices;           // CSR
     const int32_t *colptr, *rowidx, *csc_edge; // CSC: row index and CSR edge id of each entry
+    const uint4 *colsig;                       // per column: up to 8 row indices as uint16 (0xFFFF = none); NULL if a column has > 8
     const float *prior;
     const uint32_t *logmask;                   // per column: bit b = logical row b contains the column
 };

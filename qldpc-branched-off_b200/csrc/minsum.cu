@@ -54,12 +54,16 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
     uint4 *chk = reinterpret_cast<uint4 *>(smem_raw + (size_t)g.n_pad * S * sizeof(float));  // [S][m_pad]
     uint32_t *syn = reinterpret_cast<uint32_t *>(chk + (size_t)S * g.m_pad);        // [S][mw]
     uint32_t *par = syn + S * g.mw;                                                  // [S][mw]
+    int *s_rptr = reinterpret_cast<int *>(par + S * g.mw);                           // slice pointers, staged once
+    int *s_cptr = s_rptr + g.n_rslices + 1;
     __shared__ int s_unsat[S];
     __shared__ int s_active[S];
     __shared__ int s_nactive;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int n_tiles = (a.B + S - 1) / S;
+    for (int i = tid; i <= g.n_rslices; i += blockDim.x) s_rptr[i] = g.rslice_ptr[i];
+    for (int i = tid; i <= g.n_cslices; i += blockDim.x) s_cptr[i] = g.cslice_ptr[i];
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int shot0 = tile * S;
@@ -99,9 +103,16 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             const float clip = it > 0 ? a.clip : INFINITY;
 
             // ---- phase A: check rows ----------------------------------------------------------
+            uint4 rfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (warp < g.n_rslices && s_rptr[warp + 1] > s_rptr[warp]) rfirst = g.row_ell4[s_rptr[warp] + lane];
             for (int rs = warp; rs < g.n_rslices; rs += nwarps) {
-                const int base = g.rslice_ptr[rs];
-                const int nch = (g.rslice_ptr[rs + 1] - base) >> 5;
+                const int base = s_rptr[rs];
+                const int nch = (s_rptr[rs + 1] - base) >> 5;
+                const uint4 cur0 = rfirst;
+                {   // prefetch the first chunk of this warp's next slice
+                    const int nrs = rs + nwarps;
+                    if (nrs < g.n_rslices && s_rptr[nrs + 1] > s_rptr[nrs]) rfirst = g.row_ell4[s_rptr[nrs] + lane];
+                }
                 if (nch == 0) continue;
                 const uint4 *ell = g.row_ell4 + base + lane;
                 const int r = rs * 32 + lane;
@@ -120,7 +131,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                         o1[s] = 0u; o2[s] = 0u; oz[s] = 0u; ow[s] = 0u; oam[s] = -1;
                     }
                 }
-                uint4 cur = ell[0];
+                uint4 cur = cur0;
                 for (int c = 0; c < nch; ++c) {
                     const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];         // prefetch next chunk
                     const uint32_t idx[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
@@ -180,15 +191,29 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             __syncthreads();
 
             // ---- phase B: variables ------------------------------------------------------------
+            uint4 cfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
+            float pfirst = 0.f;
+            if (warp < g.n_cslices) {
+                if (s_cptr[warp + 1] > s_cptr[warp]) cfirst = g.col_ell4[s_cptr[warp] + lane];
+                if (warp * 32 + lane < g.n) pfirst = g.prior[warp * 32 + lane];
+            }
             for (int cs = warp; cs < g.n_cslices; cs += nwarps) {
-                const int base = g.cslice_ptr[cs];
-                const int nch = (g.cslice_ptr[cs + 1] - base) >> 5;
+                const int base = s_cptr[cs];
+                const int nch = (s_cptr[cs + 1] - base) >> 5;
                 const uint4 *ell = g.col_ell4 + base + lane;
                 const int j = cs * 32 + lane;
                 float acc[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) acc[s] = 0.f;
-                uint4 e4 = nch ? ell[0] : make_uint4(~0u, ~0u, ~0u, ~0u);
+                uint4 e4 = cfirst;
+                const float pr = pfirst;
+                {   // prefetch the first chunk and the priors of this warp's next slice
+                    const int ncs = cs + nwarps;
+                    if (ncs < g.n_cslices) {
+                        if (s_cptr[ncs + 1] > s_cptr[ncs]) cfirst = g.col_ell4[s_cptr[ncs] + lane]; else cfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        pfirst = (ncs * 32 + lane < g.n) ? g.prior[ncs * 32 + lane] : 0.f;
+                    }
+                }
                 for (int c = 0; c < nch; ++c) {
                     const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];
                     const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
@@ -211,7 +236,6 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                     e4 = nxt;
                 }
                 if (j < g.n) {
-                    const float pr = g.prior[j];
                     uint32_t negmask = 0u;
                     float v[S];
 #pragma unroll
@@ -498,7 +522,7 @@ __global__ void syndrome_check_kernel(GraphDev g, const uint32_t *cand_bits, int
 // ------------------------------------------------------------------------------------------------
 static size_t fast_smem_bytes(const GraphDev &g, int S)
 {
-    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4;
+    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4 + (size_t)(g.n_rslices + g.n_cslices + 2) * 4;
 }
 
 int fast_shots_per_cta(const qb_decoder *dec)

@@ -109,7 +109,7 @@ __device__ void full_radix_sort(const uint32_t *keys, uint16_t *idx0, uint16_t *
 }
 
 template <int WPL>
-__global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
+__global__ void __launch_bounds__(OSD_THREADS, 5) osd0_kernel(OsdArgs P)
 {
     const GraphDev &g = P.g;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -170,8 +170,15 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
             }
         }
         // ---- 2a. histogram of |posterior| bit patterns (selection pass 1) ---------------------------
-        if (!ext_order)
-            for (int j = tid; j < n; j += blockDim.x) atomicAdd(&s_hist[__float_as_uint(fabsf(post[j])) >> SEL_SHIFT], 1u);
+        if (!ext_order) {
+            for (int j0 = tid; j0 < n; j0 += 8 * OSD_THREADS) {      // 8 independent loads in flight per thread
+                uint32_t kb[8];
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) { const int j = j0 + u8 * OSD_THREADS; kb[u8] = j < n ? (__float_as_uint(fabsf(post[j])) >> SEL_SHIFT) : 0xFFFFFFFFu; }
+#pragma unroll
+                for (int u8 = 0; u8 < 8; ++u8) if (kb[u8] != 0xFFFFFFFFu) atomicAdd(&s_hist[kb[u8]], 1u);
+            }
+        }
         __syncthreads();
 
         // ordering modes: 0 = caller-supplied, 1 = selection windows, 2 = full sort in global scratch
@@ -181,17 +188,48 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
         uint32_t *hist = s_hist; uint16_t *off = s_off; uint32_t *listK = s_listK; uint16_t *listI = s_listI;
         const uint16_t *gsorted = nullptr;
 
-        auto Tcol = [&](int x) -> uint32_t * { return x < P.tcap ? Tsm + (size_t)x * cs : Tgl + (size_t)(x - P.tcap) * cs; };
+        // T column x, word w: shared memory for x < tcap (32-bit addressing), global spill beyond
+        auto ldT = [&](int x, int w) -> uint32_t { return x < P.tcap ? Tsm[x * cs + w] : Tgl[(size_t)(x - P.tcap) * cs + w]; };
+        auto stT = [&](int x, int w, uint32_t val) { if (x < P.tcap) Tsm[x * cs + w] = val; else Tgl[(size_t)(x - P.tcap) * cs + w] = val; };
+        auto xorT = [&](int x, int w, uint32_t val) { if (x < P.tcap) Tsm[x * cs + w] ^= val; else Tgl[(size_t)(x - P.tcap) * cs + w] ^= val; };
         auto order_at = [&](int c) -> int {
             if (mode == 0) return ext_order[c];
             if (mode == 2) return (int)gsorted[c];
             return (int)ord[c - win_start];
         };
+        // every warp keeps its own register copy of the transformed syndrome and of the non-pivot-row
+        // mask (lane = word) and updates them identically, so the termination test needs no barrier
+        uint32_t svr[WPL], npr[WPL];
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) { svr[i] = sv[lane + 32 * i]; npr[i] = npmask[lane + 32 * i]; }
         auto unresolved = [&]() -> bool {
             bool any = false;
 #pragma unroll
-            for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; any |= (sv[w] & npmask[w]) != 0u; }
+            for (int i = 0; i < WPL; ++i) any |= (svr[i] & npr[i]) != 0u;
             return __any_sync(0xFFFFFFFFu, any);
+        };
+        // reduce column j against the current T (lane = word)
+        auto reduce_column = [&](int j, uint32_t (&v)[WPL]) {
+#pragma unroll
+            for (int i = 0; i < WPL; ++i) v[i] = 0u;
+            auto add_row = [&](int r) {
+                const int pc = pivcol_of_row[r];
+                if (pc >= 0) {
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) v[i] ^= ldT(pc, w); }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) if ((r >> 5) == lane + 32 * i) v[i] ^= 1u << (r & 31);
+                }
+            };
+            if (g.colsig) {
+                const uint4 sg = g.colsig[j];
+                const uint32_t rr[8] = {sg.x & 0xFFFFu, sg.x >> 16, sg.y & 0xFFFFu, sg.y >> 16, sg.z & 0xFFFFu, sg.z >> 16, sg.w & 0xFFFFu, sg.w >> 16};
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) if (rr[k2] != 0xFFFFu) add_row((int)rr[k2]);
+            } else {
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) add_row(g.rowidx[p]);
+            }
         };
 
         int t = 0;
@@ -241,13 +279,19 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
                     mode = 2;                                          // a single bin exceeds SEL_CAP: full sort
                 } else {
                     // scatter (unordered inside a bin), then rank inside each bin by (key, index)
-                    for (int j = tid; j < n; j += blockDim.x) {
-                        const uint32_t key = __float_as_uint(fabsf(post[j]));
-                        const int b = key >> SEL_SHIFT;
-                        if (b >= bin_next && b <= bin_hi) {
-                            const uint32_t left = atomicSub(&hist[b], 1u);      // count down: consumed bins end at 0
-                            const int slot = off[b] + (int)left - 1;
-                            listK[slot] = key; listI[slot] = (uint16_t)j;
+                    for (int j0 = tid; j0 < n; j0 += 8 * OSD_THREADS) {
+                        uint32_t kb[8];
+#pragma unroll
+                        for (int u8 = 0; u8 < 8; ++u8) { const int j = j0 + u8 * OSD_THREADS; kb[u8] = j < n ? __float_as_uint(fabsf(post[j])) : 0xFFFFFFFFu; }
+#pragma unroll
+                        for (int u8 = 0; u8 < 8; ++u8) {
+                            const uint32_t key = kb[u8];
+                            const int b = key >> SEL_SHIFT;
+                            if (key != 0xFFFFFFFFu && b >= bin_next && b <= bin_hi) {
+                                const uint32_t left = atomicSub(&hist[b], 1u);      // count down: consumed bins end at 0
+                                const int slot = off[b] + (int)left - 1;
+                                listK[slot] = key; listI[slot] = (uint16_t)(j0 + u8 * OSD_THREADS);
+                            }
                         }
                     }
                     __syncthreads();
@@ -286,26 +330,11 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
 #pragma unroll
             for (int i = 0; i < WPL; ++i) v[i] = 0u;
             int myj = 0;
-            if (have) {
-                const int j = order_at(c);
-                myj = j;
-                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) {
-                    const int r = g.rowidx[p];
-                    const int pc = pivcol_of_row[r];
-                    if (pc >= 0) {
-                        const uint32_t *col = Tcol(pc);
-#pragma unroll
-                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) v[i] ^= col[w]; }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < WPL; ++i) if ((r >> 5) == lane + 32 * i) v[i] ^= 1u << (r & 31);
-                    }
-                }
-            }
+            if (have) { myj = order_at(c); reduce_column(myj, v); }
             while (true) {
                 bool f_ = false;
 #pragma unroll
-                for (int i = 0; i < WPL; ++i) f_ |= (v[i] & npmask[lane + 32 * i]) != 0u;
+                for (int i = 0; i < WPL; ++i) f_ |= (v[i] & npr[i]) != 0u;
                 const bool flag = __any_sync(0xFFFFFFFFu, f_);
                 if (lane == 0) s_flags[warp] = flag ? 1 : 0;
                 __syncthreads();
@@ -318,7 +347,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) {
                         const int w = lane + 32 * i;
-                        uint32_t bits = v[i] & npmask[w];
+                        uint32_t bits = v[i] & npr[i];
                         while (bits) {
                             const int b = __ffs(bits) - 1; bits &= bits - 1;
                             const int r = w * 32 + b;
@@ -327,12 +356,11 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
                     }
                     for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
                     const int q = best >> 16, rho = best & 0xFFFF;
-                    uint32_t *col = Tcol(t);
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) {
                         const int w = lane + 32 * i;
                         if (w < mw) {
-                            col[w] = v[i];                                    // T.e_rho after this step
+                            stT(t, w, v[i]);                                  // T.e_rho after this step
                             pv[w] = ((rho >> 5) == w) ? (v[i] & ~(1u << (rho & 31))) : v[i];
                         }
                         v[i] = 0u;
@@ -343,7 +371,6 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
                         pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
                         pivcol_of_row[rho] = (int16_t)t;
                         piv_row[t] = (uint16_t)rho; piv_pos[t] = (uint16_t)c; piv_col[t] = (uint16_t)myj;
-                        npmask[rho >> 5] &= ~(1u << (rho & 31));
                         s_rho = rho;
                     }
                 } else if (warp < f) {
@@ -367,26 +394,31 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
                         for (int i = 0; i < WPL; ++i) v[i] ^= u[i];
                     }
                 }
-                // (b) stored columns of earlier pivots: 32 columns are tested per shared-memory read
+                // (b) the transformed syndrome and the non-pivot mask (register copies, all warps)
+                {
+                    uint32_t mine = 0u;
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) if (i == ri) mine = svr[i];
+                    if (__shfl_sync(0xFFFFFFFFu, mine, rl) & rbit) {
+#pragma unroll
+                        for (int i = 0; i < WPL; ++i) svr[i] ^= u[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) if (i == ri && lane == rl) npr[i] &= ~rbit;
+                }
+                // (c) stored columns of earlier pivots; column x is only ever updated by warp (x/32) % NW, so
+                // successive pivots need no barrier between their updates.  32 columns are tested per read.
                 for (int x0 = warp * 32; x0 < t; x0 += NW * 32) {
                     const int x = x0 + lane;
-                    const bool has = x < t && (Tcol(x)[rw] & rbit) != 0u;
+                    const bool has = x < t && (ldT(x, rw) & rbit) != 0u;
                     uint32_t msk = __ballot_sync(0xFFFFFFFFu, has);
                     while (msk) {
                         const int b = __ffs(msk) - 1; msk &= msk - 1;
-                        uint32_t *col = Tcol(x0 + b);
 #pragma unroll
-                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) col[w] ^= u[i]; }
+                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) xorT(x0 + b, w, u[i]); }
                     }
                 }
-                // (c) the transformed syndrome
-                if (warp == NW - 1 && (sv[rw] & rbit)) {
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) sv[w] ^= u[i]; }
-                }
                 ++t;
-                __syncthreads();
                 done = !unresolved();
                 if (done || t >= P.rank_cap) break;
             }
@@ -396,6 +428,11 @@ __global__ void __launch_bounds__(OSD_THREADS, 4) osd0_kernel(OsdArgs P)
         }
 
         // ---- 5. solution = hard ^ e, e[ordering[pivot_col]] = s_reduced[pivot_row] ---------------
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < WPL; ++i) sv[lane + 32 * i] = svr[i];
+        }
+        __syncthreads();
         uint32_t *hard_rw = P.a.hard_bits + (size_t)shot * g.nw;
         for (int i = tid; i < t; i += blockDim.x) {
             const int rho = piv_row[i];
@@ -426,13 +463,15 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     const size_t budget = (size_t)dec->max_smem_optin - 1024;
     const size_t colb = sizeof(uint32_t) * (size_t)P.cstride;
     const size_t want = colb * (size_t)P.rank_cap;
-    // aim for 4 CTAs per SM; T columns beyond the shared-memory share spill to global memory
-    size_t share = budget / 4 > fixed ? budget / 4 - fixed : 0;
+    // aim for 5 CTAs per SM (1 KB of shared memory per CTA is reserved by the system); T columns beyond the
+    // shared-memory share spill to global memory
+    const size_t per_cta = ((size_t)dec->max_smem_optin + 1024) / 5 - 1024 - 256;
+    size_t share = per_cta > fixed ? per_cta - fixed : 0;
     size_t regionX = std::max(sel_b, std::min(want, share));
     size_t smem = fixed + regionX;
     QB_REQUIRE(smem <= budget, "OSD: problem too large for shared memory");
     P.tcap = (int)std::min<size_t>(P.rank_cap, regionX / colb);
-    const int ctas_per_sm = std::max(1, std::min(4, (int)(budget / smem)));
+    const int ctas_per_sm = std::max(1, std::min(5, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
     const int grid = std::max(1, std::min(a.F, dec->sm_count * ctas_per_sm));
     const size_t spill = (size_t)(P.rank_cap - P.tcap) * P.cstride * sizeof(uint32_t);
     const size_t b_hist = sizeof(uint32_t) * SEL_BINS, b_off = sizeof(uint16_t) * (SEL_BINS + 2);
