@@ -2,6 +2,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cmath>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -163,6 +165,15 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
         for (int j = s * 32; j < std::min(n, s * 32 + 32); ++j) deg = std::max(deg, colptr[j + 1] - colptr[j]);
         csp[s + 1] = csp[s] + ceil_div(deg, 4) * 32;
     }
+    std::vector<uint8_t> rexact(std::max(1, g.n_rslices), 0);
+    for (int r = 0; r < m; ++r) if (indptr[r + 1] - indptr[r] == 1) rexact[r >> 5] = 1;
+    g.nan_anywhere = 0;
+    for (int j = 0; j < n; ++j) if (!std::isfinite(prior[j])) g.nan_anywhere = 1;
+    {   // a variable on two degree-1 rows can receive +inf and -inf -> NaN posterior: exact path everywhere
+        std::vector<int> deg1(n, 0);
+        for (int r = 0; r < m; ++r) if (indptr[r + 1] - indptr[r] == 1 && ++deg1[indices[indptr[r]]] > 1) d->graph_nan = 1;
+        g.nan_anywhere |= d->graph_nan;
+    }
     std::vector<uint16_t> row_ell((size_t)rsp.back() * 8 + 8, 0xFFFFu);
     std::vector<uint32_t> col_ell((size_t)csp.back() * 4 + 4, 0xFFFFFFFFu);
     if (d->fast_ok) {
@@ -202,6 +213,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     UP(csc_edge, p32, g.csc_edge) UP(logmask, pu32, g.logmask)
     if (!rc) { rc = to_device(d->owned, pf, &pfl); g.prior = pfl; d->d_prior = pfl; }
     g.colsig = nullptr;
+    { uint8_t *p8 = nullptr; if (!rc) { rc = to_device(d->owned, rexact, &p8); g.rslice_exact = p8; } }
     if (!rc && !colsig.empty()) { rc = to_device(d->owned, colsig, &p16); g.colsig = reinterpret_cast<const uint4 *>(p16); }
 #undef UP
     if (rc) { qb_decoder_destroy(d); return rc; }
@@ -214,7 +226,8 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     QB_REQUIRE(dec && prior, "NULL argument");
     QB_CUDA(cudaSetDevice(dec->device));
     std::vector<float> pf(dec->g.n);
-    for (int j = 0; j < dec->g.n; ++j) pf[j] = (float)prior[j];
+    dec->g.nan_anywhere = dec->graph_nan;
+    for (int j = 0; j < dec->g.n; ++j) { pf[j] = (float)prior[j]; if (!std::isfinite(prior[j])) dec->g.nan_anywhere = 1; }
     if (dec->g.n) QB_CUDA(cudaMemcpy(dec->d_prior, pf.data(), sizeof(float) * pf.size(), cudaMemcpyHostToDevice));
     return QB_OK;
 }

@@ -39,7 +39,7 @@ struct Scratch {
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int MS_THREADS = 512;      // min-sum CTA size (16 warps)
-constexpr int MS_MAX_ROW_DEG = 57;   // sign bits + argmin + total sign must fit two 32-bit words
+constexpr int MS_MAX_ROW_DEG = 56;   // 56 sign bits + 6-bit argmin must fit two 32-bit words
 constexpr int OSD_THREADS = 128;
 constexpr int OSD_MAX_WPL = 4;       // syndrome words per lane -> m <= 4096
 
@@ -53,6 +53,8 @@ struct GraphDev {
     // lane's row / column, so a warp reads one coalesced 512-byte line per chunk.
     const int32_t *rslice_ptr;
     const uint4 *row_ell4;
+    const uint8_t *rslice_exact;               // slice contains a row of degree 1 (inf messages possible)
+    int nan_anywhere;                          // non-finite priors: every slice takes the exact path
     const int32_t *cslice_ptr;
     const uint4 *col_ell4;
     // plain CSR / CSC (general kernels, OSD)
@@ -70,6 +72,7 @@ struct qb_decoder {
     qb::GraphDev g{};
     int max_row_deg = 0, max_col_deg = 0;
     bool fast_ok = false;       // fast (on-chip message) min-sum kernel applicable
+    int graph_nan = 0;          // graph structure alone can produce NaN posteriors
     std::vector<int32_t> h_indptr, h_indices, h_colptr, h_rowidx;
     std::vector<void *> owned;  // device allocations freed on destroy
     float *d_prior = nullptr;

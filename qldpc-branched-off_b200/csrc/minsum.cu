@@ -43,8 +43,101 @@ __device__ __forceinline__ void load_vals(const float *vals, uint32_t j, float (
 
 // Check state (uint4 per check and shot):
 //   x = alpha*min1, y = alpha*min2 (float bits)
-//   z = sign of R for row positions 0..31 (already multiplied by the row's total sign)
-//   w = bits 0..24: sign of R for positions 32..56, bits 25..30: argmin position
+//   z, w = sign of R per row position (already multiplied by the row's total sign); position p lives at bit
+//          p ^ 7 of the 64-bit word w:z (byte = chunk of 8 edges, newest edge in the low bit: the bits are
+//          collected with one funnel shift per edge); w bits 24..29 = argmin position, so row degree <= 56
+//
+// One row slice (32 check rows, one per lane) for S shots.  EXACT = the slice can see inf/NaN (a row of
+// degree 1 gives min2 = inf -> +-inf messages, and inf - inf = NaN -> 0, kernels.py:327-329; or non-finite
+// priors): that variant keeps the explicit NaN test and compares instead of using sign bits.  Everywhere
+// else |q| <= clip is finite, q is never NaN or -0.0, and sign tests reduce to moving the IEEE sign bit.
+template <int S, bool EXACT>
+__device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const uint32_t *syn, const GraphDev &g,
+                                          const uint4 *ell, uint4 cur, int nch, int r, int it, float alpha, float clip)
+{
+    uint32_t o1[S], o2[S], oz[S], ow[S];
+    int oam[S];
+    float mn1[S], mn2[S];
+    uint32_t nz[S], nw_[S];
+    int am[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        mn1[s] = INFINITY; mn2[s] = INFINITY; nz[s] = 0u; nw_[s] = 0u; am[s] = 0;
+        if (it > 0) {
+            const uint4 st = chk[s * g.m_pad + r];
+            o1[s] = st.x; o2[s] = st.y; oz[s] = st.z; ow[s] = st.w; oam[s] = (int)(st.w >> 24);
+        } else {
+            o1[s] = 0u; o2[s] = 0u; oz[s] = 0u; ow[s] = 0u; oam[s] = -1;
+        }
+    }
+    for (int c = 0; c < nch; ++c) {
+        const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];         // prefetch next chunk
+        const uint32_t idx[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
+                                 cur.z & 0xFFFFu, cur.z >> 16, cur.w & 0xFFFFu, cur.w >> 16};
+        uint32_t owc[S], nsc[S], pm[S];
+        int dlt[S];
+        const int sh = (c & 3) * 8;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            owc[s] = (c < 4 ? oz[s] : ow[s]) >> sh;
+            dlt[s] = oam[s] - c * 8;
+            nsc[s] = 0u; pm[s] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t j = idx[i];
+            if (j != 0xFFFFu) {
+                float v[S];
+                load_vals<S>(vals, j, v);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const uint32_t omag = (dlt[s] == i) ? o2[s] : o1[s];
+                    const float rold = __uint_as_float(omag ^ ((owc[s] << (24 + i)) & 0x80000000u));
+                    float q = v[s] - rold;
+                    uint32_t qb;
+                    if constexpr (EXACT) {
+                        q = (q != q) ? 0.f : q;                            // kernels.py:328-329
+                        qb = (q < 0.f) ? 0x80000000u : 0u;                 // val >= 0 -> '+', kernels.py:296
+                    } else {
+                        qb = __float_as_uint(q);
+                    }
+                    const float ab = fminf(fabsf(q), clip);                // |clip(q)|, kernels.py:330-333
+                    nsc[s] = __funnelshift_l(qb, nsc[s], 1);
+                    uint32_t lt;                                           // sign bit set iff ab < min1 (strict: first minimum wins)
+                    if constexpr (EXACT) lt = (ab < mn1[s]) ? 0x80000000u : 0u;
+                    else lt = __float_as_uint(ab - mn1[s]);
+                    pm[s] = __funnelshift_l(lt, pm[s], 1);
+                    mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
+                    mn1[s] = fminf(mn1[s], ab);
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) { nsc[s] <<= 1; pm[s] <<= 1; }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            if (pm[s]) am[s] = c * 8 + 8 - __ffs(pm[s]);               // last edge of the chunk that lowered min1
+            if (c < 4) nz[s] |= nsc[s] << sh; else nw_[s] |= nsc[s] << sh;
+        }
+        cur = nxt;
+    }
+    if (r < g.m) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t sbit = (syn[s * g.mw + (r >> 5)] >> (r & 31)) & 1u;
+            const uint32_t tot = (sbit ^ (uint32_t)(__popc(nz[s]) + __popc(nw_[s]))) & 1u;
+            const uint32_t tmask = 0u - tot;
+            uint4 st;
+            st.x = __float_as_uint(alpha * mn1[s]);
+            st.y = __float_as_uint(alpha * mn2[s]);
+            st.z = nz[s] ^ tmask;
+            st.w = ((nw_[s] ^ tmask) & 0x00FFFFFFu) | ((uint32_t)am[s] << 24);
+            chk[s * g.m_pad + r] = st;
+        }
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(MS_THREADS, 1)
 minsum_fast_kernel(GraphDev g, MinsumLaunch a)
@@ -56,6 +149,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
     uint32_t *par = syn + S * g.mw;                                                  // [S][mw]
     int *s_rptr = reinterpret_cast<int *>(par + S * g.mw);                           // slice pointers, staged once
     int *s_cptr = s_rptr + g.n_rslices + 1;
+    int *s_rflag = s_cptr + g.n_cslices + 1;                                         // row slice needs the inf/NaN-exact path
     __shared__ int s_unsat[S];
     __shared__ int s_active[S];
     __shared__ int s_nactive;
@@ -64,6 +158,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
     const int n_tiles = (a.B + S - 1) / S;
     for (int i = tid; i <= g.n_rslices; i += blockDim.x) s_rptr[i] = g.rslice_ptr[i];
     for (int i = tid; i <= g.n_cslices; i += blockDim.x) s_cptr[i] = g.cslice_ptr[i];
+    for (int i = tid; i < g.n_rslices; i += blockDim.x) s_rflag[i] = g.nan_anywhere | (int)g.rslice_exact[i];
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int shot0 = tile * S;
@@ -115,78 +210,8 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                 }
                 if (nch == 0) continue;
                 const uint4 *ell = g.row_ell4 + base + lane;
-                const int r = rs * 32 + lane;
-                uint32_t o1[S], o2[S], oz[S], ow[S];
-                int oam[S];
-                float mn1[S], mn2[S];
-                uint32_t nz[S], nw_[S];
-                int am[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    mn1[s] = INFINITY; mn2[s] = INFINITY; nz[s] = 0u; nw_[s] = 0u; am[s] = 0;
-                    if (it > 0) {
-                        const uint4 st = chk[s * g.m_pad + r];
-                        o1[s] = st.x; o2[s] = st.y; oz[s] = st.z; ow[s] = st.w; oam[s] = (int)(st.w >> 25);
-                    } else {
-                        o1[s] = 0u; o2[s] = 0u; oz[s] = 0u; ow[s] = 0u; oam[s] = -1;
-                    }
-                }
-                uint4 cur = cur0;
-                for (int c = 0; c < nch; ++c) {
-                    const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];         // prefetch next chunk
-                    const uint32_t idx[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
-                                             cur.z & 0xFFFFu, cur.z >> 16, cur.w & 0xFFFFu, cur.w >> 16};
-                    uint32_t owc[S], nsc[S];
-                    int dlt[S];
-                    const int sh = (c & 3) * 8;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        owc[s] = (c < 4 ? oz[s] : ow[s]) >> sh;
-                        dlt[s] = oam[s] - c * 8;
-                        nsc[s] = 0u;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint32_t j = idx[i];
-                        if (j != 0xFFFFu) {
-                            float v[S];
-                            load_vals<S>(vals, j, v);
-                            const int t = c * 8 + i;
-#pragma unroll
-                            for (int s = 0; s < S; ++s) {
-                                const uint32_t omag = (dlt[s] == i) ? o2[s] : o1[s];
-                                const float rold = __uint_as_float(omag ^ ((owc[s] << (31 - i)) & 0x80000000u));
-                                float q = v[s] - rold;
-                                q = (q != q) ? 0.f : q;                            // kernels.py:328-329
-                                q = fminf(fmaxf(q, -clip), clip);
-                                nsc[s] |= (__float_as_uint(q) >> (31 - i)) & (1u << i);   // val >= 0 -> '+', kernels.py:296
-                                const float ab = fabsf(q);
-                                am[s] = (ab < mn1[s]) ? t : am[s];                 // strict <: first minimum wins
-                                mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
-                                mn1[s] = fminf(mn1[s], ab);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        if (c < 4) nz[s] |= nsc[s] << sh; else nw_[s] |= nsc[s] << sh;
-                    }
-                    cur = nxt;
-                }
-                if (r < g.m) {
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const uint32_t sbit = (syn[s * g.mw + (r >> 5)] >> (r & 31)) & 1u;
-                        const uint32_t tot = (sbit ^ (uint32_t)(__popc(nz[s]) + __popc(nw_[s]))) & 1u;
-                        const uint32_t tmask = 0u - tot;
-                        uint4 st;
-                        st.x = __float_as_uint(alpha * mn1[s]);
-                        st.y = __float_as_uint(alpha * mn2[s]);
-                        st.z = nz[s] ^ tmask;
-                        st.w = ((nw_[s] ^ tmask) & 0x01FFFFFFu) | ((uint32_t)am[s] << 25);
-                        chk[s * g.m_pad + r] = st;
-                    }
-                }
+                if (s_rflag[rs]) row_slice<S, true>(vals, chk, syn, g, ell, cur0, nch, rs * 32 + lane, it, alpha, clip);
+                else row_slice<S, false>(vals, chk, syn, g, ell, cur0, nch, rs * 32 + lane, it, alpha, clip);
             }
             __syncthreads();
 
@@ -223,11 +248,11 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                         if (e != 0xFFFFFFFFu) {
                             const uint32_t cidx = e >> 8, pos = e & 63u;
                             const bool hi = pos >= 32u;
-                            const uint32_t shl = 31u - (pos & 31u);
+                            const uint32_t shl = 31u - ((pos ^ 7u) & 31u);       // position p -> bit p ^ 7 (see row_slice)
 #pragma unroll
                             for (int s = 0; s < S; ++s) {
                                 const uint4 st = chk[s * g.m_pad + cidx];
-                                const uint32_t mag = ((st.w >> 25) == pos) ? st.y : st.x;
+                                const uint32_t mag = ((st.w >> 24) == pos) ? st.y : st.x;
                                 const uint32_t word = hi ? st.w : st.z;
                                 acc[s] += __uint_as_float(mag ^ ((word << shl) & 0x80000000u));   // R_sum[col] += msg, kernels.py:316
                             }
@@ -522,7 +547,7 @@ __global__ void syndrome_check_kernel(GraphDev g, const uint32_t *cand_bits, int
 // ------------------------------------------------------------------------------------------------
 static size_t fast_smem_bytes(const GraphDev &g, int S)
 {
-    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4 + (size_t)(g.n_rslices + g.n_cslices + 2) * 4;
+    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4 + (size_t)(2 * g.n_rslices + g.n_cslices + 2) * 4;
 }
 
 int fast_shots_per_cta(const qb_decoder *dec)
