@@ -151,7 +151,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     for (int r = 0; r < m; ++r) max_rd = std::max(max_rd, indptr[r + 1] - indptr[r]);
     for (int j = 0; j < n; ++j) max_cd = std::max(max_cd, colptr[j + 1] - colptr[j]);
     d->max_row_deg = max_rd; d->max_col_deg = max_cd;
-    d->fast_ok = (n <= 65534) && (max_rd <= MS_MAX_ROW_DEG) && (m < (1 << 24));
+    d->fast_ok = (n <= 65000) && (max_rd <= MS_MAX_ROW_DEG) && (max_cd <= 255) && (m < (1 << 23));
     // sliced, chunked ELL (see GraphDev)
     g.n_rslices = g.mw; g.n_cslices = g.nw;
     std::vector<int32_t> rsp(g.n_rslices + 1, 0), csp(g.n_cslices + 1, 0);
@@ -174,8 +174,11 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
         for (int r = 0; r < m; ++r) if (indptr[r + 1] - indptr[r] == 1 && ++deg1[indices[indptr[r]]] > 1) d->graph_nan = 1;
         g.nan_anywhere |= d->graph_nan;
     }
-    std::vector<uint16_t> row_ell((size_t)rsp.back() * 8 + 8, 0xFFFFu);
-    std::vector<uint32_t> col_ell((size_t)csp.back() * 4 + 4, 0xFFFFFFFFu);
+    std::vector<uint16_t> row_ell((size_t)rsp.back() * 8 + 8, (uint16_t)g.n_pad);               // dummy +inf variable
+    std::vector<uint32_t> col_ell((size_t)csp.back() * 4 + 4, (uint32_t)g.m_pad << 8);          // dummy zero check
+    std::vector<uint8_t> rdeg(std::max(1, g.n_rslices), 0), cdeg(std::max(1, g.n_cslices), 0);
+    for (int r = 0; r < m; ++r) rdeg[r >> 5] = (uint8_t)std::max<int>(rdeg[r >> 5], std::min(255, indptr[r + 1] - indptr[r]));
+    for (int j = 0; j < n; ++j) cdeg[j >> 5] = (uint8_t)std::max<int>(cdeg[j >> 5], std::min(255, colptr[j + 1] - colptr[j]));
     if (d->fast_ok) {
         for (int r = 0; r < m; ++r)
             for (int e = indptr[r]; e < indptr[r + 1]; ++e) {
@@ -213,7 +216,9 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     UP(csc_edge, p32, g.csc_edge) UP(logmask, pu32, g.logmask)
     if (!rc) { rc = to_device(d->owned, pf, &pfl); g.prior = pfl; d->d_prior = pfl; }
     g.colsig = nullptr;
-    { uint8_t *p8 = nullptr; if (!rc) { rc = to_device(d->owned, rexact, &p8); g.rslice_exact = p8; } }
+    { uint8_t *p8 = nullptr; if (!rc) { rc = to_device(d->owned, rexact, &p8); g.rslice_exact = p8; }
+      if (!rc) { rc = to_device(d->owned, rdeg, &p8); g.rslice_deg = p8; }
+      if (!rc) { rc = to_device(d->owned, cdeg, &p8); g.cslice_deg = p8; } }
     if (!rc && !colsig.empty()) { rc = to_device(d->owned, colsig, &p16); g.colsig = reinterpret_cast<const uint4 *>(p16); }
 #undef UP
     if (rc) { qb_decoder_destroy(d); return rc; }

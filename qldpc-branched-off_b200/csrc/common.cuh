@@ -48,12 +48,14 @@ struct GraphDev {
     int m, n, nnz, k, mw, nw, m_pad, n_pad;
     int n_rslices, n_cslices;
     // sliced, chunked ELL: 32 rows (columns) per slice; slice s owns uint4 words [ptr[s], ptr[s+1]);
-    // word ptr[s] + 32*c + lane holds entries 8c..8c+7 (rows: uint16 column index, 0xFFFF = padding)
-    // resp. 4c..4c+3 (columns: uint32 check << 8 | position in row, 0xFFFFFFFF = padding) of the
+    // word ptr[s] + 32*c + lane holds entries 8c..8c+7 (rows: uint16 column index, padding = n_pad, the
+    // dummy +inf variable) resp. 4c..4c+3 (columns: uint32 check << 8 | position in row, padding =
+    // m_pad << 8, the dummy all-zero check) of the
     // lane's row / column, so a warp reads one coalesced 512-byte line per chunk.
     const int32_t *rslice_ptr;
     const uint4 *row_ell4;
     const uint8_t *rslice_exact;               // slice contains a row of degree 1 (inf messages possible)
+    const uint8_t *rslice_deg, *cslice_deg;    // largest row / column degree inside the slice
     int nan_anywhere;                          // non-finite priors: every slice takes the exact path
     const int32_t *cslice_ptr;
     const uint4 *col_ell4;

@@ -18,6 +18,7 @@
 // IEEE inf/NaN behaviour is kept (no fast-math): degree-1 checks produce +-inf messages and
 // inf-inf = NaN -> 0 exactly like kernels.py:327-329.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -41,6 +42,12 @@ __device__ __forceinline__ void load_vals(const float *vals, uint32_t j, float (
     }
 }
 
+// Shared-memory extents: one extra "dummy" variable (index n_pad, value +inf) and one extra dummy check
+// (index m_pad, all-zero state) absorb the ELL padding, so the inner loops carry no validity tests:
+// a +inf variable never lowers a minimum and has sign '+', a zero check state contributes R = +0.
+__host__ __device__ inline int vals_rows(const GraphDev &g) { return g.n_pad + 4; }
+__host__ __device__ inline int chk_rows(const GraphDev &g) { return g.m_pad + 4; }
+
 // Check state (uint4 per check and shot):
 //   x = alpha*min1, y = alpha*min2 (float bits)
 //   z, w = sign of R per row position (already multiplied by the row's total sign); position p lives at bit
@@ -49,12 +56,15 @@ __device__ __forceinline__ void load_vals(const float *vals, uint32_t j, float (
 //
 // One row slice (32 check rows, one per lane) for S shots.  EXACT = the slice can see inf/NaN (a row of
 // degree 1 gives min2 = inf -> +-inf messages, and inf - inf = NaN -> 0, kernels.py:327-329; or non-finite
-// priors): that variant keeps the explicit NaN test and compares instead of using sign bits.  Everywhere
-// else |q| <= clip is finite, q is never NaN or -0.0, and sign tests reduce to moving the IEEE sign bit.
+// priors): that variant keeps the explicit NaN test, compares instead of using sign bits and skips padding
+// explicitly.  Everywhere else |q| <= clip is finite, q is never NaN or -0.0, sign tests reduce to moving the
+// IEEE sign bit, and padding entries point at the +inf dummy variable.
 template <int S, bool EXACT>
 __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const uint32_t *syn, const GraphDev &g,
-                                          const uint4 *ell, uint4 cur, int nch, int r, int it, float alpha, float clip)
+                                          const uint4 *ell, uint4 cur, int deg, int r, int it, float alpha, float clip)
 {
+    const int crow = chk_rows(g);
+    const uint32_t dummy = (uint32_t)g.n_pad;
     uint32_t o1[S], o2[S], oz[S], ow[S];
     int oam[S];
     float mn1[S], mn2[S];
@@ -64,12 +74,13 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
     for (int s = 0; s < S; ++s) {
         mn1[s] = INFINITY; mn2[s] = INFINITY; nz[s] = 0u; nw_[s] = 0u; am[s] = 0;
         if (it > 0) {
-            const uint4 st = chk[s * g.m_pad + r];
+            const uint4 st = chk[s * crow + r];
             o1[s] = st.x; o2[s] = st.y; oz[s] = st.z; ow[s] = st.w; oam[s] = (int)(st.w >> 24);
         } else {
             o1[s] = 0u; o2[s] = 0u; oz[s] = 0u; ow[s] = 0u; oam[s] = -1;
         }
     }
+    const int nch = (deg + 7) >> 3;
     for (int c = 0; c < nch; ++c) {
         const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];         // prefetch next chunk
         const uint32_t idx[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
@@ -77,6 +88,7 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
         uint32_t owc[S], nsc[S], pm[S];
         int dlt[S];
         const int sh = (c & 3) * 8;
+        const int nvalid = min(8, deg - c * 8);                          // uniform over the warp
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             owc[s] = (c < 4 ? oz[s] : ow[s]) >> sh;
@@ -85,38 +97,41 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const uint32_t j = idx[i];
-            if (j != 0xFFFFu) {
-                float v[S];
-                load_vals<S>(vals, j, v);
+            if (i < nvalid) {
+                const uint32_t j = idx[i];
+                if (!EXACT || j != dummy) {
+                    float v[S];
+                    load_vals<S>(vals, j, v);
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const uint32_t omag = (dlt[s] == i) ? o2[s] : o1[s];
-                    const float rold = __uint_as_float(omag ^ ((owc[s] << (24 + i)) & 0x80000000u));
-                    float q = v[s] - rold;
-                    uint32_t qb;
-                    if constexpr (EXACT) {
-                        q = (q != q) ? 0.f : q;                            // kernels.py:328-329
-                        qb = (q < 0.f) ? 0x80000000u : 0u;                 // val >= 0 -> '+', kernels.py:296
-                    } else {
-                        qb = __float_as_uint(q);
+                    for (int s = 0; s < S; ++s) {
+                        const uint32_t omag = (dlt[s] == i) ? o2[s] : o1[s];
+                        const float rold = __uint_as_float(omag ^ ((owc[s] << (24 + i)) & 0x80000000u));
+                        float q = v[s] - rold;
+                        uint32_t qb;
+                        if constexpr (EXACT) {
+                            q = (q != q) ? 0.f : q;                            // kernels.py:328-329
+                            qb = (q < 0.f) ? 0x80000000u : 0u;                 // val >= 0 -> '+', kernels.py:296
+                        } else {
+                            qb = __float_as_uint(q);
+                        }
+                        const float ab = fminf(fabsf(q), clip);                // |clip(q)|, kernels.py:330-333
+                        nsc[s] = __funnelshift_l(qb, nsc[s], 1);
+                        uint32_t lt;                                           // sign bit set iff ab < min1 (strict: first minimum wins)
+                        if constexpr (EXACT) lt = (ab < mn1[s]) ? 0x80000000u : 0u;
+                        else lt = __float_as_uint(ab - mn1[s]);
+                        pm[s] = __funnelshift_l(lt, pm[s], 1);
+                        mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
+                        mn1[s] = fminf(mn1[s], ab);
                     }
-                    const float ab = fminf(fabsf(q), clip);                // |clip(q)|, kernels.py:330-333
-                    nsc[s] = __funnelshift_l(qb, nsc[s], 1);
-                    uint32_t lt;                                           // sign bit set iff ab < min1 (strict: first minimum wins)
-                    if constexpr (EXACT) lt = (ab < mn1[s]) ? 0x80000000u : 0u;
-                    else lt = __float_as_uint(ab - mn1[s]);
-                    pm[s] = __funnelshift_l(lt, pm[s], 1);
-                    mn2[s] = fminf(mn2[s], fmaxf(ab, mn1[s]));
-                    mn1[s] = fminf(mn1[s], ab);
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int s = 0; s < S; ++s) { nsc[s] <<= 1; pm[s] <<= 1; }
+                    for (int s = 0; s < S; ++s) { nsc[s] <<= 1; pm[s] <<= 1; }
+                }
             }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
+            nsc[s] <<= (8 - nvalid); pm[s] <<= (8 - nvalid);            // entry i sits at bit 7 - i of the chunk byte
             if (pm[s]) am[s] = c * 8 + 8 - __ffs(pm[s]);               // last edge of the chunk that lowered min1
             if (c < 4) nz[s] |= nsc[s] << sh; else nw_[s] |= nsc[s] << sh;
         }
@@ -133,32 +148,61 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
             st.y = __float_as_uint(alpha * mn2[s]);
             st.z = nz[s] ^ tmask;
             st.w = ((nw_[s] ^ tmask) & 0x00FFFFFFu) | ((uint32_t)am[s] << 24);
-            chk[s * g.m_pad + r] = st;
+            chk[s * crow + r] = st;
+        }
+    }
+}
+
+// R messages of one chunk (4 column entries) of the lane's variable, added in row order (kernels.py:316).
+template <int S>
+__device__ __forceinline__ void col_chunk(const uint4 *chk, int crow, uint4 e4, int nvalid, float (&acc)[S])
+{
+    const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < nvalid) {                                                // uniform over the warp
+            const uint32_t e = ent[i];
+            const uint32_t cidx = e >> 8, pos = e & 63u;
+            const bool hi = pos >= 32u;
+            const uint32_t shl = 31u - ((pos ^ 7u) & 31u);               // position p -> bit p ^ 7 (see row_slice)
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const uint4 st = chk[s * crow + cidx];
+                const uint32_t mag = ((st.w >> 24) == pos) ? st.y : st.x;
+                const uint32_t word = hi ? st.w : st.z;
+                acc[s] += __uint_as_float(mag ^ ((word << shl) & 0x80000000u));
+            }
         }
     }
 }
 
 template <int S>
-__global__ void __launch_bounds__(MS_THREADS, 1)
+__global__ void __launch_bounds__(MS_THREADS, (S <= 2 ? 2 : 1))
 minsum_fast_kernel(GraphDev g, MinsumLaunch a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *vals = reinterpret_cast<float *>(smem_raw);                               // [n_pad][S]
-    uint4 *chk = reinterpret_cast<uint4 *>(smem_raw + (size_t)g.n_pad * S * sizeof(float));  // [S][m_pad]
-    uint32_t *syn = reinterpret_cast<uint32_t *>(chk + (size_t)S * g.m_pad);        // [S][mw]
+    const int vrow = vals_rows(g), crow = chk_rows(g);
+    float *vals = reinterpret_cast<float *>(smem_raw);                               // [vrow][S]
+    uint4 *chk = reinterpret_cast<uint4 *>(smem_raw + (size_t)vrow * S * sizeof(float));     // [S][crow]
+    uint32_t *syn = reinterpret_cast<uint32_t *>(chk + (size_t)S * crow);           // [S][mw]
     uint32_t *par = syn + S * g.mw;                                                  // [S][mw]
-    int *s_rptr = reinterpret_cast<int *>(par + S * g.mw);                           // slice pointers, staged once
-    int *s_cptr = s_rptr + g.n_rslices + 1;
-    int *s_rflag = s_cptr + g.n_cslices + 1;                                         // row slice needs the inf/NaN-exact path
+    int *s_rptr = reinterpret_cast<int *>(par + S * g.mw);                           // slice tables, staged once
+    int *s_cptr = s_rptr + g.n_rslices;
+    int *s_rdeg = s_cptr + g.n_cslices;                                              // degree | exact-path flag << 8
+    int *s_cdeg = s_rdeg + g.n_rslices;
     __shared__ int s_unsat[S];
     __shared__ int s_active[S];
     __shared__ int s_nactive;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int n_tiles = (a.B + S - 1) / S;
-    for (int i = tid; i <= g.n_rslices; i += blockDim.x) s_rptr[i] = g.rslice_ptr[i];
-    for (int i = tid; i <= g.n_cslices; i += blockDim.x) s_cptr[i] = g.cslice_ptr[i];
-    for (int i = tid; i < g.n_rslices; i += blockDim.x) s_rflag[i] = g.nan_anywhere | (int)g.rslice_exact[i];
+    for (int i = tid; i < g.n_rslices; i += blockDim.x) {
+        s_rptr[i] = g.rslice_ptr[i];
+        s_rdeg[i] = (int)g.rslice_deg[i] | ((g.nan_anywhere | (int)g.rslice_exact[i]) << 8);
+    }
+    for (int i = tid; i < g.n_cslices; i += blockDim.x) { s_cptr[i] = g.cslice_ptr[i]; s_cdeg[i] = (int)g.cslice_deg[i]; }
+    // dummy variable (+inf) and dummy check (zero state)
+    if (tid < S) { vals[g.n_pad * S + tid] = INFINITY; chk[tid * crow + g.m_pad] = make_uint4(0u, 0u, 0u, 0u); }
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int shot0 = tile * S;
@@ -198,68 +242,55 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             const float clip = it > 0 ? a.clip : INFINITY;
 
             // ---- phase A: check rows ----------------------------------------------------------
-            uint4 rfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
-            if (warp < g.n_rslices && s_rptr[warp + 1] > s_rptr[warp]) rfirst = g.row_ell4[s_rptr[warp] + lane];
+            uint4 rfirst = make_uint4(0u, 0u, 0u, 0u);
+            if (warp < g.n_rslices && (s_rdeg[warp] & 255)) rfirst = g.row_ell4[s_rptr[warp] + lane];
             for (int rs = warp; rs < g.n_rslices; rs += nwarps) {
                 const int base = s_rptr[rs];
-                const int nch = (s_rptr[rs + 1] - base) >> 5;
+                const int dg = s_rdeg[rs];
                 const uint4 cur0 = rfirst;
                 {   // prefetch the first chunk of this warp's next slice
                     const int nrs = rs + nwarps;
-                    if (nrs < g.n_rslices && s_rptr[nrs + 1] > s_rptr[nrs]) rfirst = g.row_ell4[s_rptr[nrs] + lane];
+                    if (nrs < g.n_rslices && (s_rdeg[nrs] & 255)) rfirst = g.row_ell4[s_rptr[nrs] + lane];
                 }
-                if (nch == 0) continue;
+                if ((dg & 255) == 0) continue;
                 const uint4 *ell = g.row_ell4 + base + lane;
-                if (s_rflag[rs]) row_slice<S, true>(vals, chk, syn, g, ell, cur0, nch, rs * 32 + lane, it, alpha, clip);
-                else row_slice<S, false>(vals, chk, syn, g, ell, cur0, nch, rs * 32 + lane, it, alpha, clip);
+                if (dg >> 8) row_slice<S, true>(vals, chk, syn, g, ell, cur0, dg & 255, rs * 32 + lane, it, alpha, clip);
+                else row_slice<S, false>(vals, chk, syn, g, ell, cur0, dg & 255, rs * 32 + lane, it, alpha, clip);
             }
             __syncthreads();
 
             // ---- phase B: variables ------------------------------------------------------------
-            uint4 cfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
+            // the first two chunks (8 entries) and the priors of a slice are fetched one slice ahead
+            uint4 cf0 = make_uint4(0u, 0u, 0u, 0u), cf1 = cf0;
             float pfirst = 0.f;
             if (warp < g.n_cslices) {
-                if (s_cptr[warp + 1] > s_cptr[warp]) cfirst = g.col_ell4[s_cptr[warp] + lane];
+                const int d0 = s_cdeg[warp];
+                if (d0 > 0) cf0 = g.col_ell4[s_cptr[warp] + lane];
+                if (d0 > 4) cf1 = g.col_ell4[s_cptr[warp] + 32 + lane];
                 if (warp * 32 + lane < g.n) pfirst = g.prior[warp * 32 + lane];
             }
             for (int cs = warp; cs < g.n_cslices; cs += nwarps) {
                 const int base = s_cptr[cs];
-                const int nch = (s_cptr[cs + 1] - base) >> 5;
+                const int deg = s_cdeg[cs];
                 const uint4 *ell = g.col_ell4 + base + lane;
                 const int j = cs * 32 + lane;
-                float acc[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) acc[s] = 0.f;
-                uint4 e4 = cfirst;
+                const uint4 e0 = cf0, e1 = cf1;
                 const float pr = pfirst;
-                {   // prefetch the first chunk and the priors of this warp's next slice
+                {
                     const int ncs = cs + nwarps;
                     if (ncs < g.n_cslices) {
-                        if (s_cptr[ncs + 1] > s_cptr[ncs]) cfirst = g.col_ell4[s_cptr[ncs] + lane]; else cfirst = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        const int d1 = s_cdeg[ncs];
+                        if (d1 > 0) cf0 = g.col_ell4[s_cptr[ncs] + lane];
+                        if (d1 > 4) cf1 = g.col_ell4[s_cptr[ncs] + 32 + lane];
                         pfirst = (ncs * 32 + lane < g.n) ? g.prior[ncs * 32 + lane] : 0.f;
                     }
                 }
-                for (int c = 0; c < nch; ++c) {
-                    const uint4 nxt = ell[(c + 1 < nch ? c + 1 : c) * 32];
-                    const uint32_t ent[4] = {e4.x, e4.y, e4.z, e4.w};
+                float acc[S];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t e = ent[i];
-                        if (e != 0xFFFFFFFFu) {
-                            const uint32_t cidx = e >> 8, pos = e & 63u;
-                            const bool hi = pos >= 32u;
-                            const uint32_t shl = 31u - ((pos ^ 7u) & 31u);       // position p -> bit p ^ 7 (see row_slice)
-#pragma unroll
-                            for (int s = 0; s < S; ++s) {
-                                const uint4 st = chk[s * g.m_pad + cidx];
-                                const uint32_t mag = ((st.w >> 24) == pos) ? st.y : st.x;
-                                const uint32_t word = hi ? st.w : st.z;
-                                acc[s] += __uint_as_float(mag ^ ((word << shl) & 0x80000000u));   // R_sum[col] += msg, kernels.py:316
-                            }
-                        }
-                    }
-                    e4 = nxt;
-                }
+                for (int s = 0; s < S; ++s) acc[s] = 0.f;
+                if (deg > 0) col_chunk<S>(chk, crow, e0, min(4, deg), acc);
+                if (deg > 4) col_chunk<S>(chk, crow, e1, min(4, deg - 4), acc);
+                for (int c = 2; c * 4 < deg; ++c) col_chunk<S>(chk, crow, ell[c * 32], min(4, deg - c * 4), acc);
                 if (j < g.n) {
                     uint32_t negmask = 0u;
                     float v[S];
@@ -271,14 +302,14 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                     if constexpr (S == 4) *reinterpret_cast<float4 *>(vals + j * 4) = make_float4(v[0], v[1], v[2], v[3]);
                     else if constexpr (S == 2) *reinterpret_cast<float2 *>(vals + j * 2) = make_float2(v[0], v[1]);
                     else vals[j] = v[0];
-                    if (negmask) {
-                        for (int c = 0; c < nch; ++c) {
-                            const uint4 q4 = ell[c * 32];
+                    if (negmask) {                                 // hard decision 1: flip the parity of its checks
+                        for (int c = 0; c * 4 < deg; ++c) {
+                            const uint4 q4 = c == 0 ? e0 : (c == 1 ? e1 : ell[c * 32]);
                             const uint32_t ent[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                if (ent[i] == 0xFFFFFFFFu) continue;
                                 const uint32_t cidx = ent[i] >> 8;
+                                if (c * 4 + i >= deg || cidx >= (uint32_t)g.m) continue;
 #pragma unroll
                                 for (int s = 0; s < S; ++s)
                                     if (negmask & (1u << s)) atomicXor(&par[s * g.mw + (cidx >> 5)], 1u << (cidx & 31));
@@ -547,13 +578,17 @@ __global__ void syndrome_check_kernel(GraphDev g, const uint32_t *cand_bits, int
 // ------------------------------------------------------------------------------------------------
 static size_t fast_smem_bytes(const GraphDev &g, int S)
 {
-    return (size_t)g.n_pad * S * 4 + (size_t)S * g.m_pad * 16 + (size_t)2 * S * g.mw * 4 + (size_t)(2 * g.n_rslices + g.n_cslices + 2) * 4;
+    return (size_t)vals_rows(g) * S * 4 + (size_t)S * chk_rows(g) * 16 + (size_t)2 * S * g.mw * 4 + (size_t)(2 * g.n_rslices + 2 * g.n_cslices) * 4;
 }
 
 int fast_shots_per_cta(const qb_decoder *dec)
 {
     if (!dec->fast_ok) return 0;
     const int cand[3] = {4, 2, 1};
+    if (const char *e = getenv("QLDPC_B200_MS_S")) {      // tuning override
+        const int S = atoi(e);
+        if ((S == 1 || S == 2 || S == 4) && fast_smem_bytes(dec->g, S) + 1024 <= (size_t)dec->max_smem_optin) return S;
+    }
     for (int S : cand)
         if (fast_smem_bytes(dec->g, S) + 1024 <= (size_t)dec->max_smem_optin) return S;
     return 0;
@@ -565,10 +600,11 @@ static int launch_fast(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
     const size_t smem = fast_smem_bytes(dec->g, S);
     QB_CUDA(cudaFuncSetAttribute(minsum_fast_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (a.B + S - 1) / S;
-    int ctas_per_sm = std::max(1, std::min(4, (int)((size_t)dec->max_smem_optin / (smem + 1024))));
-    // thread count: enough warps for the slices, fewer for small codes so several CTAs share an SM
+    int ctas_per_sm = std::max(1, std::min(8, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
+    // thread count: 512 while at most two CTAs fit an SM, fewer for small codes so that several CTAs share it
     int threads = MS_THREADS;
-    if (ctas_per_sm >= 2) threads = 256;
+    if (ctas_per_sm > 2) threads = 256;
+    if (const char *e = getenv("QLDPC_B200_MS_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= MS_THREADS && t % 32 == 0) threads = t; }
     ctas_per_sm = std::min(ctas_per_sm, 2048 / threads);
     const int grid = std::max(1, std::min(tiles, dec->sm_count * ctas_per_sm));
     minsum_fast_kernel<S><<<grid, threads, smem, st>>>(dec->g, a);
