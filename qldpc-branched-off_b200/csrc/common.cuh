@@ -40,7 +40,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int MS_THREADS = 512;      // min-sum CTA size (16 warps)
 constexpr int MS_MAX_ROW_DEG = 56;   // 56 sign bits + 6-bit argmin must fit two 32-bit words
-constexpr int OSD_THREADS = 128;
+constexpr int OSD_THREADS = 128;      // four warps per failed side
 constexpr int OSD_MAX_WPL = 4;       // syndrome words per lane -> m <= 4096
 
 // Device view of one decoding side (what kernels receive by value).

@@ -26,11 +26,12 @@
 
 namespace qb {
 
+constexpr int OSD_CTAS_PER_SM = 7;
 constexpr int OSD_NW = OSD_THREADS / 32;   // warps per CTA = candidates reduced per round
 constexpr int SEL_BINS = 2048;             // histogram bins: float bits 30..20 (8 bins per octave)
 constexpr int SEL_SHIFT = 20;
-constexpr int SEL_CAP = 2048;              // candidates materialised per selection window
-constexpr int SEL_MIN = 512;               // a window is closed once it holds at least this many
+constexpr int SEL_CAP = 1024;              // candidates materialised per selection window
+constexpr int SEL_MIN = 384;               // a window is closed once it holds at least this many
 
 struct OsdArgs {
     GraphDev g;
@@ -47,6 +48,7 @@ struct OsdArgs {
     uint32_t *g_keys;     // [grid][n]          (full sort)
     uint16_t *g_idx;      // [grid][2][n_pad2]  (full sort)
     uint32_t *g_cnt;      // [grid][256 * OSD_NW]
+    uint16_t *g_pivpos;   // [grid][rank_cap] pivot positions in the ordering (only filled when pivots_out is set)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
@@ -109,7 +111,7 @@ __device__ void full_radix_sort(const uint32_t *keys, uint16_t *idx0, uint16_t *
 }
 
 template <int WPL>
-__global__ void __launch_bounds__(OSD_THREADS, 5) osd0_kernel(OsdArgs P)
+__global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdArgs P)
 {
     const GraphDev &g = P.g;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -124,7 +126,6 @@ __global__ void __launch_bounds__(OSD_THREADS, 5) osd0_kernel(OsdArgs P)
     uint16_t *row_at_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
     int16_t *pivcol_of_row = reinterpret_cast<int16_t *>(sp); sp += sizeof(int16_t) * g.m_pad;
     uint16_t *piv_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
-    uint16_t *piv_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // position in the ordering
     uint16_t *piv_col = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // column index
     uint32_t *npmask = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
     uint32_t *sv = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(OSD_THREADS, 5) osd0_kernel(OsdArgs P)
     uint16_t *s_listI = reinterpret_cast<uint16_t *>(s_listK + SEL_CAP);
     uint32_t *Tsm = regionX;
     uint32_t *Tgl = P.gT ? P.gT + (size_t)blockIdx.x * (size_t)(P.rank_cap - P.tcap) * cs : nullptr;
+    uint16_t *piv_pos = P.g_pivpos + (size_t)blockIdx.x * P.rank_cap;
     __shared__ int s_flags[NW];
     __shared__ int s_rho, s_binhi, s_wincount;
 
@@ -370,7 +372,8 @@ __global__ void __launch_bounds__(OSD_THREADS, 5) osd0_kernel(OsdArgs P)
                         row_at_pos[t] = (uint16_t)rho; row_at_pos[q] = (uint16_t)rt;
                         pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
                         pivcol_of_row[rho] = (int16_t)t;
-                        piv_row[t] = (uint16_t)rho; piv_pos[t] = (uint16_t)c; piv_col[t] = (uint16_t)myj;
+                        piv_row[t] = (uint16_t)rho; piv_col[t] = (uint16_t)myj;
+                        if (P.a.pivots_out) piv_pos[t] = (uint16_t)c;
                         s_rho = rho;
                     }
                 } else if (warp < f) {
@@ -458,20 +461,20 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.rank_cap = std::min(g.m, g.n);
     P.cstride = (g.mw & 1) ? g.mw : g.mw + 1;
     const int n_pad2 = (g.n + 1) & ~1;
-    const size_t fixed = sizeof(uint16_t) * 6 * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
+    const size_t fixed = sizeof(uint16_t) * 5 * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
     const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint16_t) * (SEL_BINS + 2) + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
     const size_t budget = (size_t)dec->max_smem_optin - 1024;
     const size_t colb = sizeof(uint32_t) * (size_t)P.cstride;
     const size_t want = colb * (size_t)P.rank_cap;
-    // aim for 5 CTAs per SM (1 KB of shared memory per CTA is reserved by the system); T columns beyond the
-    // shared-memory share spill to global memory
-    const size_t per_cta = ((size_t)dec->max_smem_optin + 1024) / 5 - 1024 - 256;
+    // one warp per side, OSD_CTAS_PER_SM sides in flight per SM (1 KB of shared memory per CTA is reserved by
+    // the system); T columns beyond the shared-memory share spill to global memory
+    const size_t per_cta = ((size_t)dec->max_smem_optin + 1024) / OSD_CTAS_PER_SM - 1024 - 256;
     size_t share = per_cta > fixed ? per_cta - fixed : 0;
     size_t regionX = std::max(sel_b, std::min(want, share));
     size_t smem = fixed + regionX;
     QB_REQUIRE(smem <= budget, "OSD: problem too large for shared memory");
     P.tcap = (int)std::min<size_t>(P.rank_cap, regionX / colb);
-    const int ctas_per_sm = std::max(1, std::min(5, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
+    const int ctas_per_sm = std::max(1, std::min(OSD_CTAS_PER_SM, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
     const int grid = std::max(1, std::min(a.F, dec->sm_count * ctas_per_sm));
     const size_t spill = (size_t)(P.rank_cap - P.tcap) * P.cstride * sizeof(uint32_t);
     const size_t b_hist = sizeof(uint32_t) * SEL_BINS, b_off = sizeof(uint16_t) * (SEL_BINS + 2);
@@ -479,7 +482,8 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     const size_t b_keys = sizeof(uint32_t) * (size_t)g.n, b_idx = sizeof(uint16_t) * 2 * (size_t)n_pad2, b_cnt = sizeof(uint32_t) * 256 * OSD_NW;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t G = (size_t)grid;
-    const size_t need = al(G * spill) + al(G * b_hist) + al(G * b_off) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
+    const size_t b_pp = sizeof(uint16_t) * (size_t)std::max(1, P.rank_cap);
+    const size_t need = al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_off) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
     if (int rc = dec->work.ensure(need)) return rc;
     unsigned char *p = dec->work.as<unsigned char>();
     P.gT = spill ? reinterpret_cast<uint32_t *>(p) : nullptr; p += al(G * spill);
@@ -489,7 +493,8 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.g_listI = reinterpret_cast<uint16_t *>(p); p += al(G * b_li);
     P.g_keys = reinterpret_cast<uint32_t *>(p); p += al(G * b_keys);
     P.g_idx = reinterpret_cast<uint16_t *>(p); p += al(G * b_idx);
-    P.g_cnt = reinterpret_cast<uint32_t *>(p);
+    P.g_cnt = reinterpret_cast<uint32_t *>(p); p += al(G * b_cnt);
+    P.g_pivpos = reinterpret_cast<uint16_t *>(p);
     QB_CUDA(cudaFuncSetAttribute(osd0_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     osd0_kernel<WPL><<<grid, OSD_THREADS, smem, st>>>(P);
     QB_CUDA(cudaGetLastError());
