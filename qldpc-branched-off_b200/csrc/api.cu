@@ -431,6 +431,7 @@ int qb_osd0_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h
     OsdLaunch a{};
     a.syn_bits = d_syn; a.hard_bits = d_hard; a.post = d_post; a.ordering = ordering_h ? d_ord : nullptr;
     a.fail_idx = nullptr; a.F = B; a.rank_out = d_rank; a.pivots_out = d_piv;
+    a.exact_rows = 1;        // arbitrary (possibly inconsistent) syndromes: reproduce the reference's pivot rows
     if (int rc = launch_osd0(dec, a, 0)) return rc;
     const size_t cnt = sB * g.n;
     if (cnt) {

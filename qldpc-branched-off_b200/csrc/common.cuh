@@ -131,6 +131,7 @@ struct OsdLaunch {
     const int32_t *n_fail_d;    // nullable device count
     int32_t *rank_out;          // nullable [B]
     int32_t *pivots_out;        // nullable [B][min(m,n)]
+    int exact_rows;             // emulate the reference's pivot-row order (inconsistent syndromes)
 };
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
 

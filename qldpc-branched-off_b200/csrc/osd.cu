@@ -20,13 +20,15 @@
 //      pivots would get e = 0 (their s_reduced entries can no longer change), so the result equals
 //      the full sweep bit for bit while typically needing ~150 instead of ~930 pivots;
 //   5. flips hard[ordering[pivot_col]] where s_reduced[pivot_row] = 1   (osd.py:19-25).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace qb {
 
-constexpr int OSD_CTAS_PER_SM = 7;
+constexpr int OSD_CTAS_PER_SM = 9;
 constexpr int OSD_NW = OSD_THREADS / 32;   // warps per CTA = candidates reduced per round
 constexpr int SEL_BINS = 2048;             // histogram bins: float bits 30..20 (8 bins per octave)
 constexpr int SEL_SHIFT = 20;
@@ -42,7 +44,6 @@ struct OsdArgs {
     uint32_t *gT;         // [grid][(rank_cap - tcap) * cstride] spill
     // per-CTA global scratch for the rare paths: later selection windows and the full-sort fallback
     uint32_t *g_hist;     // [grid][SEL_BINS]
-    uint16_t *g_off;      // [grid][SEL_BINS + 1]
     uint32_t *g_listK;    // [grid][SEL_CAP]
     uint16_t *g_listI;    // [grid][SEL_CAP]
     uint32_t *g_keys;     // [grid][n]          (full sort)
@@ -110,7 +111,10 @@ __device__ void full_radix_sort(const uint32_t *keys, uint16_t *idx0, uint16_t *
     }
 }
 
-template <int WPL>
+// EXACTROWS: choose each pivot row exactly like the reference's swapped row order (needed only when the
+// syndrome may be inconsistent, i.e. outside the column space of H, where the result depends on it);
+// for consistent syndromes -- every simulated shot -- the solution is unique and the lowest free row is used.
+template <int WPL, bool EXACTROWS>
 __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdArgs P)
 {
     const GraphDev &g = P.g;
@@ -122,8 +126,11 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
 
     // ---- shared memory carve-up -------------------------------------------------------------------
     unsigned char *sp = smem_raw;
-    uint16_t *pos_of_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
-    uint16_t *row_at_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
+    uint16_t *pos_of_row = nullptr, *row_at_pos = nullptr;
+    if (EXACTROWS) {
+        pos_of_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
+        row_at_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
+    }
     int16_t *pivcol_of_row = reinterpret_cast<int16_t *>(sp); sp += sizeof(int16_t) * g.m_pad;
     uint16_t *piv_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
     uint16_t *piv_col = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // column index
@@ -133,9 +140,8 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
     uint16_t *ord = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * SEL_CAP;   // current window, sorted
     uint32_t *regionX = reinterpret_cast<uint32_t *>(sp);
     // selection scratch of the first window overlays T (T is empty until the first pivot)
-    uint32_t *s_hist = regionX;
-    uint16_t *s_off = reinterpret_cast<uint16_t *>(s_hist + SEL_BINS);
-    uint32_t *s_listK = reinterpret_cast<uint32_t *>(s_off + SEL_BINS + 2);
+    uint32_t *s_hist = regionX;                 // per bin: low 16 bits = count still to place, high 16 = window offset
+    uint32_t *s_listK = s_hist + SEL_BINS;
     uint16_t *s_listI = reinterpret_cast<uint16_t *>(s_listK + SEL_CAP);
     uint32_t *Tsm = regionX;
     uint32_t *Tgl = P.gT ? P.gT + (size_t)blockIdx.x * (size_t)(P.rank_cap - P.tcap) * cs : nullptr;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
             else if (w * 32 < m) full = (1u << (m - w * 32)) - 1u;
             npmask[w] = full;
         }
-        for (int r = tid; r < g.m_pad; r += blockDim.x) { pos_of_row[r] = (uint16_t)r; row_at_pos[r] = (uint16_t)r; pivcol_of_row[r] = -1; }
+        for (int r = tid; r < g.m_pad; r += blockDim.x) { if (EXACTROWS) { pos_of_row[r] = (uint16_t)r; row_at_pos[r] = (uint16_t)r; } pivcol_of_row[r] = -1; }
         if (!ext_order) for (int b = tid; b < SEL_BINS; b += blockDim.x) s_hist[b] = 0u;
         __syncthreads();
         for (int w = tid; w < g.nw; w += blockDim.x) {
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         int mode = ext_order ? 0 : 1;
         int bin_next = 0;                 // first histogram bin not yet consumed
         int win_start = 0, win_end = ext_order ? n : 0;
-        uint32_t *hist = s_hist; uint16_t *off = s_off; uint32_t *listK = s_listK; uint16_t *listI = s_listI;
+        uint32_t *hist = s_hist; uint32_t *listK = s_listK; uint16_t *listI = s_listI;
         const uint16_t *gsorted = nullptr;
 
         // T column x, word w: shared memory for x < tcap (32-bit addressing), global spill beyond
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
             // ---- 2b. materialise the next window of candidates, sorted by (|posterior|, index) --------
             if (c0 >= win_end && mode == 1) {
                 if (t > 0) {       // T now lives in regionX: later windows use the global scratch
-                    hist = P.g_hist + (size_t)blockIdx.x * SEL_BINS; off = P.g_off + (size_t)blockIdx.x * (SEL_BINS + 2);
+                    hist = P.g_hist + (size_t)blockIdx.x * SEL_BINS;
                     listK = P.g_listK + (size_t)blockIdx.x * SEL_CAP; listI = P.g_listI + (size_t)blockIdx.x * SEL_CAP;
                     for (int b = tid; b < SEL_BINS; b += blockDim.x) hist[b] = 0u;
                     __syncthreads();
@@ -256,10 +262,10 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                     bool stop = false;
                     for (int b0 = bin_next; b0 < SEL_BINS && !stop; b0 += 32) {
                         const int b = b0 + lane;
-                        const int cnt = b < SEL_BINS ? (int)hist[b] : 0;
+                        const int cnt = b < SEL_BINS ? (int)(hist[b] & 0xFFFFu) : 0;
                         int inc = cnt;
                         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
-                        if (b < SEL_BINS) off[b] = (uint16_t)min(cum + inc - cnt, 65535);
+                        if (b < SEL_BINS) hist[b] = ((uint32_t)min(cum + inc - cnt, 65535) << 16) | (uint32_t)cnt;
                         const uint32_t over = __ballot_sync(0xFFFFFFFFu, cum + inc > SEL_CAP);
                         const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum + inc >= SEL_MIN);
                         int last = 31;
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                             const uint32_t key = kb[u8];
                             const int b = key >> SEL_SHIFT;
                             if (key != 0xFFFFFFFFu && b >= bin_next && b <= bin_hi) {
-                                const uint32_t left = atomicSub(&hist[b], 1u);      // count down: consumed bins end at 0
-                                const int slot = off[b] + (int)left - 1;
+                                const uint32_t old = atomicSub(&hist[b], 1u);       // count down: consumed bins end at count 0
+                                const int slot = (int)(old >> 16) + (int)(old & 0xFFFFu) - 1;
                                 listK[slot] = key; listI[slot] = (uint16_t)(j0 + u8 * OSD_THREADS);
                             }
                         }
@@ -301,9 +307,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                         const uint32_t key = listK[i];
                         const uint16_t id = listI[i];
                         const int b = key >> SEL_SHIFT;
-                        const int lo = off[b];
+                        const int lo = (int)(hist[b] >> 16);
                         int hi2 = M;
-                        if (b < bin_hi) { int bb = b + 1; hi2 = off[bb]; }   // off[] is non-decreasing over the window
+                        if (b < bin_hi) hi2 = (int)(hist[b + 1] >> 16);       // offsets are non-decreasing over the window
                         int rank = lo;
                         for (int k2 = lo; k2 < hi2; ++k2) {
                             const uint32_t kk = listK[k2];
@@ -344,20 +350,25 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                 if (fb == 0u) break;
                 const int f = __ffs(fb) - 1;
                 if (warp == f) {
-                    // pivot row = first row, in the reference's current (swapped) row order, with the bit set
+                    // pivot row: EXACTROWS = first row, in the reference's current (swapped) row order, with the
+                    // bit set; otherwise the lowest free row with the bit set
                     uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) {
                         const int w = lane + 32 * i;
                         uint32_t bits = v[i] & npr[i];
-                        while (bits) {
-                            const int b = __ffs(bits) - 1; bits &= bits - 1;
-                            const int r = w * 32 + b;
-                            best = min(best, ((uint32_t)pos_of_row[r] << 16) | (uint32_t)r);
+                        if (EXACTROWS) {
+                            while (bits) {
+                                const int b = __ffs(bits) - 1; bits &= bits - 1;
+                                const int r = w * 32 + b;
+                                best = min(best, ((uint32_t)pos_of_row[r] << 16) | (uint32_t)r);
+                            }
+                        } else if (bits) {
+                            best = min(best, (uint32_t)(w * 32 + __ffs(bits) - 1));
                         }
                     }
                     for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-                    const int q = best >> 16, rho = best & 0xFFFF;
+                    const int q = EXACTROWS ? (int)(best >> 16) : 0, rho = best & 0xFFFF;
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) {
                         const int w = lane + 32 * i;
@@ -368,9 +379,11 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                         v[i] = 0u;
                     }
                     if (lane == 0) {
-                        const int rt = row_at_pos[t];
-                        row_at_pos[t] = (uint16_t)rho; row_at_pos[q] = (uint16_t)rt;
-                        pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
+                        if (EXACTROWS) {
+                            const int rt = row_at_pos[t];
+                            row_at_pos[t] = (uint16_t)rho; row_at_pos[q] = (uint16_t)rt;
+                            pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
+                        }
                         pivcol_of_row[rho] = (int16_t)t;
                         piv_row[t] = (uint16_t)rho; piv_col[t] = (uint16_t)myj;
                         if (P.a.pivots_out) piv_pos[t] = (uint16_t)c;
@@ -452,7 +465,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
     }
 }
 
-template <int WPL>
+template <int WPL, bool EXACTROWS>
 static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
 {
     const GraphDev &g = dec->g;
@@ -461,42 +474,43 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.rank_cap = std::min(g.m, g.n);
     P.cstride = (g.mw & 1) ? g.mw : g.mw + 1;
     const int n_pad2 = (g.n + 1) & ~1;
-    const size_t fixed = sizeof(uint16_t) * 5 * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
-    const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint16_t) * (SEL_BINS + 2) + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
+    const size_t fixed = sizeof(uint16_t) * (EXACTROWS ? 5 : 3) * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
+    const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
     const size_t budget = (size_t)dec->max_smem_optin - 1024;
     const size_t colb = sizeof(uint32_t) * (size_t)P.cstride;
     const size_t want = colb * (size_t)P.rank_cap;
     // one warp per side, OSD_CTAS_PER_SM sides in flight per SM (1 KB of shared memory per CTA is reserved by
     // the system); T columns beyond the shared-memory share spill to global memory
-    const size_t per_cta = ((size_t)dec->max_smem_optin + 1024) / OSD_CTAS_PER_SM - 1024 - 256;
+    int target = OSD_CTAS_PER_SM;
+    if (const char *e = getenv("QLDPC_B200_OSD_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= OSD_CTAS_PER_SM) target = v; }
+    const size_t per_cta = ((size_t)dec->max_smem_optin + 1024) / target - 1024 - 256;
     size_t share = per_cta > fixed ? per_cta - fixed : 0;
     size_t regionX = std::max(sel_b, std::min(want, share));
     size_t smem = fixed + regionX;
     QB_REQUIRE(smem <= budget, "OSD: problem too large for shared memory");
     P.tcap = (int)std::min<size_t>(P.rank_cap, regionX / colb);
-    const int ctas_per_sm = std::max(1, std::min(OSD_CTAS_PER_SM, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
+    const int ctas_per_sm = std::max(1, std::min(target, (int)(((size_t)dec->max_smem_optin + 1024) / (smem + 1024))));
     const int grid = std::max(1, std::min(a.F, dec->sm_count * ctas_per_sm));
     const size_t spill = (size_t)(P.rank_cap - P.tcap) * P.cstride * sizeof(uint32_t);
-    const size_t b_hist = sizeof(uint32_t) * SEL_BINS, b_off = sizeof(uint16_t) * (SEL_BINS + 2);
+    const size_t b_hist = sizeof(uint32_t) * SEL_BINS;
     const size_t b_lk = sizeof(uint32_t) * SEL_CAP, b_li = sizeof(uint16_t) * SEL_CAP;
     const size_t b_keys = sizeof(uint32_t) * (size_t)g.n, b_idx = sizeof(uint16_t) * 2 * (size_t)n_pad2, b_cnt = sizeof(uint32_t) * 256 * OSD_NW;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t G = (size_t)grid;
     const size_t b_pp = sizeof(uint16_t) * (size_t)std::max(1, P.rank_cap);
-    const size_t need = al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_off) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
+    const size_t need = al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
     if (int rc = dec->work.ensure(need)) return rc;
     unsigned char *p = dec->work.as<unsigned char>();
     P.gT = spill ? reinterpret_cast<uint32_t *>(p) : nullptr; p += al(G * spill);
     P.g_hist = reinterpret_cast<uint32_t *>(p); p += al(G * b_hist);
-    P.g_off = reinterpret_cast<uint16_t *>(p); p += al(G * b_off);
     P.g_listK = reinterpret_cast<uint32_t *>(p); p += al(G * b_lk);
     P.g_listI = reinterpret_cast<uint16_t *>(p); p += al(G * b_li);
     P.g_keys = reinterpret_cast<uint32_t *>(p); p += al(G * b_keys);
     P.g_idx = reinterpret_cast<uint16_t *>(p); p += al(G * b_idx);
     P.g_cnt = reinterpret_cast<uint32_t *>(p); p += al(G * b_cnt);
     P.g_pivpos = reinterpret_cast<uint16_t *>(p);
-    QB_CUDA(cudaFuncSetAttribute(osd0_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    osd0_kernel<WPL><<<grid, OSD_THREADS, smem, st>>>(P);
+    QB_CUDA(cudaFuncSetAttribute(osd0_kernel<WPL, EXACTROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    osd0_kernel<WPL, EXACTROWS><<<grid, OSD_THREADS, smem, st>>>(P);
     QB_CUDA(cudaGetLastError());
     return QB_OK;
 }
@@ -511,11 +525,19 @@ int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     }
     if (!a.ordering && !a.post) { set_error("OSD-0 needs posteriors or an ordering"); return QB_ERR_ARG; }
     const int wpl = ceil_div(g.mw, 32);
+    if (a.exact_rows) {
+        switch (wpl) {
+            case 1: return launch_osd_wpl<1, true>(dec, a, st);
+            case 2: return launch_osd_wpl<2, true>(dec, a, st);
+            case 3: return launch_osd_wpl<3, true>(dec, a, st);
+            default: return launch_osd_wpl<4, true>(dec, a, st);
+        }
+    }
     switch (wpl) {
-        case 1: return launch_osd_wpl<1>(dec, a, st);
-        case 2: return launch_osd_wpl<2>(dec, a, st);
-        case 3: return launch_osd_wpl<3>(dec, a, st);
-        default: return launch_osd_wpl<4>(dec, a, st);
+        case 1: return launch_osd_wpl<1, false>(dec, a, st);
+        case 2: return launch_osd_wpl<2, false>(dec, a, st);
+        case 3: return launch_osd_wpl<3, false>(dec, a, st);
+        default: return launch_osd_wpl<4, false>(dec, a, st);
     }
 }
 
