@@ -430,3 +430,42 @@ def test_steane_code_capacity_smoke():
     L = g["L"]
     errs = int((((det @ L) % 2) != ((E @ L) % 2)).sum())
     assert int((~conv).sum()) == int(g["nonconverged"]) and errs == int(g["logical_errors"])
+
+
+# ---- BASELINE configs 4 and 5: other codes through the same pipeline ---------------------------------------
+def _host_events(ft, B, p, seed):
+    rng = np.random.default_rng(seed)
+    fired = rng.random((B, ft.L)) < p
+    sh, loc = np.nonzero(fired)
+    kind = ft.loc_kind[loc]
+    out = np.where(kind == 3, rng.integers(0, 15, len(loc)), np.where(kind == 2, rng.integers(0, 3, len(loc)), 0))
+    ev_ptr = np.zeros(B + 1, dtype=np.int64); np.add.at(ev_ptr, sh + 1, 1)
+    return np.cumsum(ev_ptr).astype(np.int32), (loc.astype(np.uint32) | (out.astype(np.uint32) << 24)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("tag,p,max_iter,B", [("90", 0.004, 20, 48), ("108", 0.006, 20, 48), ("288", 0.006, 100, 6)])
+def test_other_codes_pipeline_vs_oracle(tag, p, max_iter, B):
+    """Configs 4/5: [[90,8,10]], [[108,8,10]] (p sweep) and [[288,12,18]] at high max-iter + OSD: syndromes from
+    host-sampled faults (K2), then per side converged / iterations exact and logical flags vs the oracle."""
+    from qldpc_b200.simulation.engine import ShotEngine
+    s = code_setup(tag); M = matrices(tag, p)
+    ev_ptr, ev = _host_events(s["ft"], B, p, seed=int(tag))
+    eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=64)
+    cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC)
+    counts, flags, conv, fin = eng.pipeline.run_events(ev_ptr, ev, cfg, want_detail=True)
+    sz, tz, sx, tx = eng.sampler.syndromes_from_events(ev_ptr, ev)
+    m, k = M["first_logical_rowZ"], s["Lx"].shape[0]
+    gz = orc.SideGraph(M["HdecZ"], M["HZ_full"][m:m + k], orc.llr_priors(M["channel_probsZ"]))
+    gx = orc.SideGraph(M["HdecX"], M["HX_full"][m:m + k], orc.llr_priors(M["channel_probsX"]))
+    agree = tot = 0
+    for i in range(B):
+        for sd, g, syn, tl in ((0, gz, sz[i], tz[i]), (1, gx, sx[i], tx[i])):
+            err, cv, its = orc.decode_side(g, syn, tl, max_iter)
+            assert cv == bool(conv[sd][i]) and its == fin[sd][i] + 1, (tag, i, sd)
+            mine = bool((flags[i] >> sd) & 1)
+            if cv:
+                assert mine == err
+            agree += mine == err; tot += 1
+    assert agree / tot >= 0.9
+    assert counts[3] == B
+    eng.close()
