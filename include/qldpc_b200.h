@@ -91,6 +91,13 @@ int qb_minsum_decode_host(qb_decoder *dec, const int8_t *syndrome_h, int32_t B, 
 int qb_minsum_core_host(qb_decoder *dec, const double *Q_h, const double *syndrome_sign_h, int32_t B,
                         double alpha, double *R_h, double *Rsum_h);
 
+/* Check-to-variable messages for the Alvarado alpha estimators (src/decoding/alpha.py:122-137, :206-253):
+ * for each of B syndromes (int8 [B][m]) advance the min-sum decoder n_prev iterations with alpha_prev_h[0..n_prev)
+ * (no convergence stop; damping and clip as in alpha.py:217-243), then return the unscaled (alpha = 1)
+ * messages of the next check pass, R_h double [B][nnz] in CSR edge order.  prior_h double [n]. */
+int qb_alpha_messages_host(qb_decoder *dec, const int8_t *syndrome_h, int32_t B, const double *prior_h, int32_t n_prev,
+                           const double *alpha_prev_h, double damping, double clip_llr, double *R_h);
+
 /* tanh/atanh sum-product decoder: performBeliefPropagationFast + bp_core
  * (src/decoding/dense.py:75-96, src/decoding/kernels.py:172-193). */
 int qb_bp_decode_host(qb_decoder *dec, const int8_t *syndrome_h, int32_t B, int32_t max_iter,

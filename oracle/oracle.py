@@ -279,3 +279,26 @@ def llr_priors(channel_probs):
     with np.errstate(divide="ignore", invalid="ignore"):
         cp = np.asarray(channel_probs, dtype=np.float64)
         return np.clip(np.nan_to_num(np.log((1 - cp) / cp)), -50, 50)
+
+
+def alpha_messages(H_csr, syndromes, prior, alpha_prev, damping=1.0, clip_llr=20.0):
+    """Oracle for the message collection of src/decoding/alpha.py:206-253 (autoregressive; with an empty
+    ``alpha_prev`` it is the single-iteration case :127-137): advance with the given alphas, no convergence
+    stop, then the unscaled check pass.  Returns R [B, nnz]."""
+    indices, indptr = _i32(H_csr.indices), _i32(H_csr.indptr)
+    m, n = H_csr.shape
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    out = []
+    for syn in np.asarray(syndromes).reshape(-1, m):
+        ss = np.ascontiguousarray(1.0 - 2.0 * syn.astype(np.float64))
+        Q = np.ascontiguousarray(prior[indices])
+        Qold = Q.copy()
+        for a in alpha_prev:
+            R, Rs = minsum_core_sparse(None, indices, indptr, Q, ss, float(a), m, n)
+            q = (Rs + prior)[indices] - R
+            q = np.where(np.isnan(q), 0.0, np.clip(q, -clip_llr, clip_llr))
+            Q = np.clip(damping * q + (1.0 - damping) * Qold, -clip_llr, clip_llr)
+            Qold = Q.copy()
+        R, _ = minsum_core_sparse(None, indices, indptr, Q, ss, 1.0, m, n)
+        out.append(R)
+    return np.array(out)

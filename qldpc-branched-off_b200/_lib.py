@@ -39,7 +39,7 @@ class PipelineStats(C.Structure):
 
 EXPORTS = [
     "qb_last_error", "qb_device_count", "qb_version", "qb_decoder_create", "qb_decoder_set_prior",
-    "qb_decoder_destroy", "qb_minsum_batch", "qb_minsum_decode_host", "qb_minsum_core_host", "qb_bp_decode_host",
+    "qb_decoder_destroy", "qb_minsum_batch", "qb_minsum_decode_host", "qb_minsum_core_host", "qb_alpha_messages_host", "qb_bp_decode_host",
     "qb_syndrome_check_host", "qb_osd0_batch", "qb_osd0_host", "qb_gf2_eliminate_host", "qb_sampler_create",
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
@@ -159,6 +159,16 @@ class Decoder:
         R = np.zeros((B, self.nnz)); Rs = np.zeros((B, self.n))
         check(load().qb_minsum_core_host(self._h, ptr(Q), ptr(ss), B, c_double(alpha), ptr(R), ptr(Rs)))
         return R, Rs
+
+    def alpha_messages(self, syndromes, prior, alpha_prev, damping=1.0, clip_llr=20.0):
+        """Unscaled check messages after len(alpha_prev) full iterations (reference alpha.py:206-253)."""
+        syn = np.ascontiguousarray(syndromes, dtype=np.int8).reshape(-1, self.m)
+        prior = np.ascontiguousarray(prior, dtype=np.float64)
+        ap = np.ascontiguousarray(alpha_prev, dtype=np.float64).reshape(-1)
+        R = np.zeros((syn.shape[0], self.nnz), dtype=np.float64)
+        check(load().qb_alpha_messages_host(self._h, ptr(syn), syn.shape[0], ptr(prior), len(ap), ptr(ap) if len(ap) else None,
+                                            c_double(damping), c_double(clip_llr), ptr(R)))
+        return R
 
     def bp(self, syndromes, max_iter):
         syn = np.ascontiguousarray(syndromes, dtype=np.int8).reshape(-1, self.m)

@@ -40,6 +40,8 @@ int launch_bp(qb_decoder *dec, const uint32_t *syn_bits, int B, int max_iter, ui
 int launch_syndrome_check(qb_decoder *dec, const uint32_t *cand_bits, int B, uint32_t *syn_bits, cudaStream_t st);
 int launch_gf2_dense(uint32_t *A, uint32_t *b, int m, int n, int nw, int32_t *pr, int32_t *pc, int32_t *np, cudaStream_t st);
 int fast_shots_per_cta(const qb_decoder *dec);
+int launch_alpha_messages(qb_decoder *dec, const int8_t *syn, int B, int n_prev, const double *alpha_prev_d, double damping,
+                          double clip, const double *prior64_d, double *R_out, cudaStream_t st);
 
 template <class T>
 static int to_device(std::vector<void *> &owned, const std::vector<T> &h, T **out)
@@ -336,6 +338,27 @@ int qb_minsum_core_host(qb_decoder *dec, const double *Q_h, const double *ssign_
     if (int rc = launch_minsum_core(dec, dQ, dS, B, alpha, dR, dRs, 0)) return rc;
     if (g.nnz) QB_CUDA(cudaMemcpy(R_h, dR, sB * g.nnz * 8, cudaMemcpyDeviceToHost));
     if (g.n) QB_CUDA(cudaMemcpy(Rsum_h, dRs, sB * g.n * 8, cudaMemcpyDeviceToHost));
+    return QB_OK;
+}
+
+int qb_alpha_messages_host(qb_decoder *dec, const int8_t *syndrome_h, int32_t B, const double *prior_h, int32_t n_prev,
+                           const double *alpha_prev_h, double damping, double clip_llr, double *R_h)
+{
+    QB_REQUIRE(dec && syndrome_h && prior_h && R_h && n_prev >= 0 && (n_prev == 0 || alpha_prev_h), "bad argument");
+    if (B <= 0) return QB_OK;
+    QB_CUDA(cudaSetDevice(dec->device));
+    const GraphDev &g = dec->g;
+    const size_t sB = (size_t)B;
+    if (int rc = dec->scratch.ensure(carve_size({sB * g.m, (size_t)g.n * 8, (size_t)std::max(1, n_prev) * 8, sB * g.nnz * 8}))) return rc;
+    Carver cv(dec->scratch.ptr);
+    int8_t *d_syn = cv.take<int8_t>(sB * g.m);
+    double *d_prior = cv.take<double>(g.n), *d_alpha = cv.take<double>(std::max(1, n_prev)), *d_R = cv.take<double>(sB * g.nnz);
+    if (g.m) QB_CUDA(cudaMemcpy(d_syn, syndrome_h, sB * g.m, cudaMemcpyHostToDevice));
+    if (g.n) QB_CUDA(cudaMemcpy(d_prior, prior_h, (size_t)g.n * 8, cudaMemcpyHostToDevice));
+    if (n_prev) QB_CUDA(cudaMemcpy(d_alpha, alpha_prev_h, (size_t)n_prev * 8, cudaMemcpyHostToDevice));
+    if (g.nnz) QB_CUDA(cudaMemset(d_R, 0, sB * g.nnz * 8));
+    if (int rc = launch_alpha_messages(dec, d_syn, B, n_prev, d_alpha, damping, clip_llr, d_prior, d_R, 0)) return rc;
+    if (g.nnz) QB_CUDA(cudaMemcpy(R_h, d_R, sB * g.nnz * 8, cudaMemcpyDeviceToHost));
     return QB_OK;
 }
 

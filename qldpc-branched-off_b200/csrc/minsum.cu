@@ -489,6 +489,62 @@ __global__ void minsum_core_kernel(GraphDev g, const double *Q, const double *ss
     }
 }
 
+// Messages for the Alvarado alpha estimators (src/decoding/alpha.py:122-137 and :206-253): advance the
+// decoder n_prev iterations with the given alphas (no convergence stop, damping / clip like the decoder,
+// alpha.py:217-243), then one unscaled check pass (alpha = 1) whose messages R are returned.
+// Double precision like the reference's pre-pass.  ws per slot: Q[nnz], R[nnz] doubles.
+__global__ void __launch_bounds__(256)
+alpha_messages_kernel(GraphDev g, const int8_t *syndrome, int B, int n_prev, const double *alpha_prev,
+                      double damping, double clip, const double *prior64, double *R_out, double *ws)
+{
+    const int tid = threadIdx.x;
+    double *Q = ws + (size_t)blockIdx.x * 2 * (size_t)g.nnz;
+    double *R = Q + g.nnz;
+    for (int shot = blockIdx.x; shot < B; shot += gridDim.x) {
+        const int8_t *syn = syndrome + (size_t)shot * g.m;
+        for (int e = tid; e < g.nnz; e += blockDim.x) Q[e] = prior64[g.indices[e]];
+        __syncthreads();
+        for (int it = 0; it <= n_prev; ++it) {
+            const bool final_pass = (it == n_prev);
+            const double alpha = final_pass ? 1.0 : alpha_prev[it];
+            double *Rdst = final_pass ? R_out + (size_t)shot * g.nnz : R;
+            for (int r = tid; r < g.m; r += blockDim.x) {
+                const int rs = g.indptr[r], re = g.indptr[r + 1];
+                if (rs == re) continue;
+                double sp = 1.0 - 2.0 * (double)syn[r], mn1 = INFINITY, mn2 = INFINITY;
+                int mp = -1;
+                for (int e = rs; e < re; ++e) {
+                    const double v = Q[e];
+                    sp *= (v >= 0) ? 1.0 : -1.0;
+                    const double ab = fabs(v);
+                    if (ab < mn1) { mn2 = mn1; mn1 = ab; mp = e; } else if (ab < mn2) mn2 = ab;
+                }
+                for (int e = rs; e < re; ++e) {
+                    const double sj = (Q[e] >= 0) ? 1.0 : -1.0;
+                    Rdst[e] = alpha * (sp * sj) * ((e == mp) ? mn2 : mn1);
+                }
+            }
+            __syncthreads();
+            if (final_pass) break;
+            for (int j = tid; j < g.n; j += blockDim.x) {
+                double acc = 0.0;
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) acc += R[g.csc_edge[p]];
+                const double v = acc + prior64[j];
+                for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) {
+                    const int e = g.csc_edge[p];
+                    double q = v - R[e];
+                    if (q != q) q = 0.0; else if (q > clip) q = clip; else if (q < -clip) q = -clip;
+                    double qd = damping * q + (1.0 - damping) * Q[e];
+                    if (qd > clip) qd = clip; else if (qd < -clip) qd = -clip;
+                    Q[e] = qd;
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
 // tanh/atanh BP (dense.py:75-96, kernels.py:172-193), double precision; ws per slot: Q[nnz], R[nnz], vals[n]
 __global__ void __launch_bounds__(256)
 bp_kernel(GraphDev g, const uint32_t *syn_bits, int B, int max_iter, uint32_t *hard_bits, uint8_t *converged,
@@ -634,6 +690,18 @@ int launch_minsum_core(qb_decoder *dec, const double *Q, const double *ssign, in
 {
     if (B <= 0) return QB_OK;
     minsum_core_kernel<<<B, 256, 0, st>>>(dec->g, Q, ssign, B, alpha, R, Rsum);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_alpha_messages(qb_decoder *dec, const int8_t *syn, int B, int n_prev, const double *alpha_prev_d, double damping,
+                          double clip, const double *prior64_d, double *R_out, cudaStream_t st)
+{
+    if (B <= 0) return QB_OK;
+    const GraphDev &g = dec->g;
+    const int slots = std::max(1, std::min(B, dec->sm_count * 8));
+    if (int rc = dec->work.ensure((size_t)slots * 2 * (size_t)std::max(1, g.nnz) * sizeof(double))) return rc;
+    alpha_messages_kernel<<<slots, 256, 0, st>>>(g, syn, B, n_prev, alpha_prev_d, damping, clip, prior64_d, R_out, dec->work.as<double>());
     QB_CUDA(cudaGetLastError());
     return QB_OK;
 }

@@ -86,27 +86,55 @@ class ShotEngine:
         self.pipeline.close(); self.decZ.close(); self.decX.close(); self.sampler.close()
 
 
-def _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha):
+def _estimation_trials(n_cols, error_rate, alpha_estimation_trials):
+    """Dynamic trial count of engine.py:233-247: enough samples of true-1 bits for the histogram."""
+    dynamic = max(500, min(50000, int(2000 / (n_cols * error_rate))))
+    return alpha_estimation_trials if alpha_estimation_trials != 5000 else dynamic
+
+
+def _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha, matrices, llrs_z, llrs_x, error_rate, maxIter,
+                 alpha_estimation_trials, alpha_estimation_bins, plot_dir):
+    """alpha-mode handling of engine.py:216-344 -> (mode name, QB mode, alpha_z, alpha_x, extra result fields)."""
+    extras = {}
     if alpha_mode is None:
         alpha_mode = "dynamical" if use_dynamic_alpha else "alvarado"
+    fmt = lambda r: f"{r:.6g}".replace(".", "p")
     if alpha_mode == "dynamical":
-        return alpha_mode, _lib.QB_ALPHA_DYNAMIC, 1.0, 1.0
+        return alpha_mode, _lib.QB_ALPHA_DYNAMIC, 1.0, 1.0, extras
     if alpha_mode == "alvarado":
         if alvarado_alpha is None:
-            raise NotImplementedError("Alvarado alpha estimation pre-pass (reference src/decoding/alpha.py) is not part "
-                                      "of the GPU hot path yet; pass alvarado_alpha=(alpha_z, alpha_x)")
-        if isinstance(alvarado_alpha, (list, tuple, np.ndarray)) and len(alvarado_alpha) == 2:
+            from ..decoding.alpha import estimate_alpha_alvarado
+            tz = _estimation_trials(np.asarray(matrices["HdecZ"]).shape[1], error_rate, alpha_estimation_trials)
+            tx = _estimation_trials(np.asarray(matrices["HdecX"]).shape[1], error_rate, alpha_estimation_trials)
+            _logger.info("Alpha estimation trials: Z=%d, X=%d (dynamic based on n*p)", tz, tx)
+            az, r2z = estimate_alpha_alvarado(matrices["HdecZ"], error_rate, trials=tz, bins=alpha_estimation_bins, plot_dir=plot_dir,
+                                              plot_prefix=f"alvarado_{fmt(error_rate)}_z", llrs=llrs_z)
+            ax, r2x = estimate_alpha_alvarado(matrices["HdecX"], error_rate, trials=tx, bins=alpha_estimation_bins, plot_dir=plot_dir,
+                                              plot_prefix=f"alvarado_{fmt(error_rate)}_x", llrs=llrs_x)
+            extras.update(alpha_r2_z=r2z, alpha_r2_x=r2x)
+        elif isinstance(alvarado_alpha, (list, tuple, np.ndarray)) and len(alvarado_alpha) == 2:
             az, ax = float(alvarado_alpha[0]), float(alvarado_alpha[1])
+            extras.update(alpha_r2_z=None, alpha_r2_x=None)
         else:
             az = ax = float(alvarado_alpha)
+            extras.update(alpha_r2_z=None, alpha_r2_x=None)
+        _logger.info("Alvarado alpha for p=%.6g: alpha_z=%.6g, alpha_x=%.6g", error_rate, az, ax)
         if az <= 0 or ax <= 0:
             raise ValueError("alpha must be > 0 when alpha_mode='alvarado'")
-        return alpha_mode, _lib.QB_ALPHA_FIXED, az, ax
+        return alpha_mode, _lib.QB_ALPHA_FIXED, az, ax, extras
     if alpha_mode == "alvarado-autoregressive":
         if alvarado_alpha is not None:
             raise ValueError("alvarado_alpha must be None for alvarado-autoregressive")
-        raise NotImplementedError("autoregressive alpha estimation pre-pass (reference src/decoding/alpha.py:160-276) "
-                                  "is not part of the GPU hot path yet; use run_shots(alpha_seq_z=..., alpha_seq_x=...)")
+        from ..decoding.alpha import estimate_alpha_alvarado_autoregressive
+        tz = _estimation_trials(np.asarray(matrices["HdecZ"]).shape[1], error_rate, alpha_estimation_trials)
+        tx = _estimation_trials(np.asarray(matrices["HdecX"]).shape[1], error_rate, alpha_estimation_trials)
+        _logger.info("Autoregressive alpha estimation trials: Z=%d, X=%d (dynamic based on n*p)", tz, tx)
+        az, r2z = estimate_alpha_alvarado_autoregressive(matrices["HdecZ"], error_rate, maxIter=maxIter, trials=tz, bins=alpha_estimation_bins,
+                                                         plot_dir=plot_dir, plot_prefix=f"autoregressive_{fmt(error_rate)}_z", llrs=llrs_z)
+        ax, r2x = estimate_alpha_alvarado_autoregressive(matrices["HdecX"], error_rate, maxIter=maxIter, trials=tx, bins=alpha_estimation_bins,
+                                                         plot_dir=plot_dir, plot_prefix=f"autoregressive_{fmt(error_rate)}_x", llrs=llrs_x)
+        extras.update(alpha_values_z=az, alpha_values_x=ax, alpha_r2_values_z=r2z, alpha_r2_values_x=r2x)
+        return alpha_mode, _lib.QB_ALPHA_SEQUENCE, az, ax, extras
     raise ValueError(f"Unsupported alpha_mode: {alpha_mode}")
 
 
@@ -119,11 +147,19 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
         raise NotImplementedError("SCOPT beta estimation (reference scopt.py) is outside the GPU hot path")
     if base_seed is None:
         base_seed = np.random.randint(0, 2 ** 31)
-    alpha_mode, qmode, alpha_z, alpha_x = _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha)
+    if alpha_mode not in (None, "dynamical", "alvarado", "alvarado-autoregressive"):
+        raise ValueError(f"Unsupported alpha_mode: {alpha_mode}")
     cb = BBCodeCircuit(Hx, Hz, num_cycles=num_cycles, **bb_params)
     compiled = CompiledCircuit.from_builder(cb)
     ft = fault_tables_for(compiled, Lx, Lz)
     matrices = precomputed_matrices or matrices_from_tables(ft, error_rate, num_cycles)
+    if estimation_plot_dir is not None:
+        import os
+        os.makedirs(estimation_plot_dir, exist_ok=True)
+    alpha_mode, qmode, alpha_z, alpha_x, extras = _alpha_setup(
+        alpha_mode, use_dynamic_alpha, alvarado_alpha, matrices, llr_priors(matrices["channel_probsZ"]),
+        llr_priors(matrices["channel_probsX"]), error_rate, maxIter, alpha_estimation_trials, alpha_estimation_bins,
+        estimation_plot_dir)
     if max_trials is None:
         max_trials = num_trials if num_trials is not None else 1000000
     stop_on_errors = target_logical_errors is not None and target_logical_errors > 0
@@ -154,13 +190,15 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
             done += round_total
     finally:
         eng.close()
-    return {
+    result = {
         "logical_error_rate": tot_errs / max(1, trials_run),
         "z_logical_error_rate": z_errs / max(1, trials_run),
         "x_logical_error_rate": x_errs / max(1, trials_run),
         "num_trials": trials_run,
         "logical_errors": tot_errs,
     }
+    result.update(extras)          # alpha_values_* / alpha_r2_* like engine.py:474-481
+    return result
 
 
 def _reduce_counts(dist, counts):

@@ -235,12 +235,31 @@ def steane_fixture():
     print("steane: nonconverged", nonconv, "logical errors", errs)
 
 
+def alpha_fixture():
+    """Alvarado alpha estimators (src/decoding/alpha.py) on the 72 code with seeded generators."""
+    from src.decoding.alpha import estimate_alpha_alvarado, estimate_alpha_alvarado_autoregressive
+    name, p = "[[72, 12, 6]]", 0.004
+    d, bb = load_code(name)
+    M = load_matrices(os.path.join(REF, "matrix_cache"), compute_cache_key(d["Hx"], d["Hz"], d["Lx"], d["Lz"], int(d["distance"]), p))
+    out = {"p": p}
+    for sd, H, cp in (("z", M["HdecZ"], M["channel_probsZ"]), ("x", M["HdecX"], M["channel_probsX"])):
+        ll = llrs(cp)
+        a, r2 = estimate_alpha_alvarado(H, p, trials=60, bins=50, rng=np.random.default_rng(5), llrs=ll)
+        out[f"alv_{sd}"] = np.array([a, r2])
+        av, rv = estimate_alpha_alvarado_autoregressive(H, p, maxIter=4, trials=40, bins=50, rng=np.random.default_rng(6), llrs=ll)
+        out[f"auto_{sd}"] = np.array([av, rv])
+        print("alpha", sd, a, r2, av, rv, flush=True)
+    np.savez_compressed(os.path.join(HERE, "alpha_72.npz"), **out)
+
+
 if __name__ == "__main__":
     # numba 0.65 cannot type np.clip on scalars inside bp_core (kernels.py:191), so the reference's
     # performBeliefPropagationFast does not compile here; run the same source un-jitted instead.
     import src.decoding.dense as _dense
     _dense.bp_core = rk.bp_core.py_func
-    which = sys.argv[1:] or ["builder", "small", "steane", "72", "144"]
+    which = sys.argv[1:] or ["builder", "small", "steane", "72", "144", "alpha"]
+    if "alpha" in which:
+        alpha_fixture()
     if "builder" in which:
         builder_fixture()
     if "small" in which:

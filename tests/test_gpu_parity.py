@@ -469,3 +469,43 @@ def test_other_codes_pipeline_vs_oracle(tag, p, max_iter, B):
     assert agree / tot >= 0.9
     assert counts[3] == B
     eng.close()
+
+
+# ---- alpha estimation pre-pass ----------------------------------------------------------
+def test_alpha_messages_vs_oracle_and_reference_alphas():
+    """qb_alpha_messages_host against the oracle restatement of alpha.py:206-253, and the full estimators
+    against the alphas the real reference produced with the same seeded generators (tests/golden/alpha_72.npz)."""
+    from qldpc_b200.decoding.alpha import estimate_alpha_alvarado, estimate_alpha_alvarado_autoregressive
+    g = np.load(os.path.join(GOLDEN, "alpha_72.npz")); p = float(g["p"]); M = matrices("72", p)
+    for sd, H, cp in (("z", M["HdecZ"], M["channel_probsZ"]), ("x", M["HdecX"], M["channel_probsX"])):
+        Hc = csr_matrix(H); prior = orc.llr_priors(cp)
+        dec = _lib.cached_decoder(Hc.indptr, Hc.indices, H.shape[1], prior)
+        rng = np.random.default_rng(1)
+        errs = (rng.random((5, H.shape[1])) < 0.01).astype(np.int8)
+        syn = ((errs @ H.T) % 2).astype(np.int8)
+        for prev in ([], [0.5], [0.4, 0.7, 0.9]):
+            mine = dec.alpha_messages(syn, prior, np.array(prev))
+            ref = orc.alpha_messages(Hc, syn, prior, prev)
+            assert np.array_equal(np.isinf(mine), np.isinf(ref))
+            f = np.isfinite(ref)
+            np.testing.assert_allclose(mine[f], ref[f], rtol=0, atol=1e-12)
+        a, r2 = estimate_alpha_alvarado(H, p, trials=60, bins=50, rng=np.random.default_rng(5), llrs=prior)
+        np.testing.assert_allclose([a, r2], g[f"alv_{sd}"], rtol=1e-6, atol=1e-8)
+        av, rv = estimate_alpha_alvarado_autoregressive(H, p, maxIter=4, trials=40, bins=50, rng=np.random.default_rng(6), llrs=prior)
+        np.testing.assert_allclose(av, g[f"auto_{sd}"][0], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(rv, g[f"auto_{sd}"][1], rtol=1e-6, atol=1e-8)
+
+
+def test_run_simulation_alvarado_autoregressive_mode():
+    """main.py's default alpha_mode (main.py:48) end to end: estimation pre-pass + decoding with the sequence."""
+    from qldpc_b200.simulation.engine import run_simulation
+    s = code_setup("72"); p = 0.005
+    res = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=3000, num_cycles=6, maxIter=6, osd_order=2,
+                         precomputed_matrices=matrices("72", p), alpha_mode="alvarado-autoregressive", base_seed=3,
+                         alpha_estimation_trials=300, **s["bb"])
+    assert res["num_trials"] == 3000 and 0.1 < res["logical_error_rate"] < 0.8
+    assert len(res["alpha_values_z"]) == 6 and len(res["alpha_values_x"]) == 6 and len(res["alpha_r2_values_z"]) == 6
+    assert all(0.1 < a < 1.5 for a in res["alpha_values_z"])
+    res2 = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=1000, num_cycles=6, maxIter=6,
+                          alpha_mode="alvarado", base_seed=3, alpha_estimation_trials=300, **s["bb"])
+    assert 0.1 < res2["logical_error_rate"] < 0.8 and res2["alpha_r2_z"] is not None

@@ -161,3 +161,21 @@ def test_oracle_steane_smoke():
             det = orc.performOSD_enhanced(H, syn, values, hard, order=0)
         errs += int(((L @ det) % 2) != ((L @ E[i]) % 2))
     assert nonconv == int(g["nonconverged"]) and errs == int(g["logical_errors"])
+
+
+def test_oracle_alpha_messages_reproduce_reference_alphas():
+    """The oracle's message collection (alpha.py:206-253 restated) + the host fit reproduce the alphas the real
+    reference computed with the same seeded generators."""
+    from qldpc_b200.decoding.alpha import _estimate_alpha_from_samples
+    g = np.load(os.path.join(GOLDEN, "alpha_72.npz")); p = float(g["p"]); M = matrices("72", p)
+    H = M["HdecZ"]; Hc = csr_matrix(H); prior = orc.llr_priors(M["channel_probsZ"])
+    rng = np.random.default_rng(5)
+    t0, t1 = [], []
+    for _ in range(60):
+        e = (rng.random(H.shape[1]) < p).astype(np.int8)
+        syn = (Hc.dot(e) % 2).astype(np.int8)
+        R = orc.alpha_messages(Hc, syn[None, :], prior, [])[0]
+        bits = e[Hc.indices].astype(bool)
+        t0.append(R[~bits]); t1.append(R[bits])
+    a, r2 = _estimate_alpha_from_samples(np.concatenate(t0), np.concatenate(t1), bins=50)
+    np.testing.assert_allclose([a, r2], g["alv_z"], rtol=1e-7, atol=1e-9)
