@@ -49,6 +49,7 @@ struct OsdArgs {
     uint32_t *g_keys;     // [grid][n]          (full sort)
     uint16_t *g_idx;      // [grid][2][n_pad2]  (full sort)
     uint32_t *g_cnt;      // [grid][256 * OSD_NW]
+    int32_t *work_counter; // device counter, zero at launch
     uint16_t *g_pivpos;   // [grid][rank_cap] pivot positions in the ordering (only filled when pivots_out is set)
 };
 
@@ -151,7 +152,14 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
 
     const int F = P.a.n_fail_d ? min(*P.a.n_fail_d, P.a.F) : P.a.F;
 
-    for (int qi = blockIdx.x; qi < F; qi += gridDim.x) {
+    __shared__ int s_qi;
+    while (true) {
+        // dynamic work distribution: per-side cost varies by more than an order of magnitude
+        if (tid == 0) s_qi = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int qi = s_qi;
+        __syncthreads();
+        if (qi >= F) break;
         const int shot = P.a.fail_idx ? P.a.fail_idx[qi] : qi;
         const uint32_t *hard = P.a.hard_bits + (size_t)shot * g.nw;
         const int32_t *ext_order = P.a.ordering ? P.a.ordering + (size_t)shot * n : nullptr;
@@ -498,9 +506,11 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t G = (size_t)grid;
     const size_t b_pp = sizeof(uint16_t) * (size_t)std::max(1, P.rank_cap);
-    const size_t need = al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
+    const size_t need = 256 + al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
     if (int rc = dec->work.ensure(need)) return rc;
     unsigned char *p = dec->work.as<unsigned char>();
+    P.work_counter = reinterpret_cast<int32_t *>(p); p += 256;
+    QB_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int32_t), st));
     P.gT = spill ? reinterpret_cast<uint32_t *>(p) : nullptr; p += al(G * spill);
     P.g_hist = reinterpret_cast<uint32_t *>(p); p += al(G * b_hist);
     P.g_listK = reinterpret_cast<uint32_t *>(p); p += al(G * b_lk);
