@@ -6,7 +6,7 @@
 Workload (BASELINE.json configs[2]): [[144,12,12]] gross code, circuit-level p = 0.005, min-sum
 20 iterations (dynamical alpha) + OSD-0 on non-converged sides, both sides per shot.
 A step = one pass of the whole hot path (Philox sampling -> syndromes -> min-sum Z,X -> OSD-0 ->
-logical check) over --shots-per-step shots per GPU.  One JSON line on stdout (rank 0).
+logical check) over --shots-per-step shots per GPU (one device batch of --batch shots by default).  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -109,7 +109,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shots-per-step", type=int, default=65536)
-    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -205,10 +205,17 @@ def main():
     sets = []
     kind = ft.loc_kind
     for _ in range(n_sets):
-        fired = rng.random((Be, ft.L)) < P
-        sh, loc = np.nonzero(fired)
+        # i.i.d. Bernoulli(P) over the Be x L (shot, location) grid by geometric skipping (exact, and cheap on the host)
+        total = Be * ft.L
+        gaps = rng.geometric(P, size=int(total * P * 1.05) + 1000)
+        pos = np.cumsum(gaps) - 1
+        while pos[-1] < total:
+            more = np.cumsum(rng.geometric(P, size=len(gaps) // 10 + 1000)) + pos[-1]
+            pos = np.concatenate([pos, more])
+        pos = pos[pos < total]
+        sh, loc = np.divmod(pos, ft.L)
         out = np.where(kind[loc] == 3, rng.integers(0, 15, len(loc)), np.where(kind[loc] == 2, rng.integers(0, 3, len(loc)), 0))
-        evp = np.zeros(Be + 1, dtype=np.int32); np.add.at(evp, sh + 1, 1); evp = np.cumsum(evp).astype(np.int32)
+        evp = np.zeros(Be + 1, dtype=np.int64); np.add.at(evp, sh + 1, 1); evp = np.cumsum(evp).astype(np.int32)
         ev = (loc.astype(np.uint32) | (out.astype(np.uint32) << 24)).astype(np.uint32)
         pp = torch.empty(len(evp), dtype=torch.int32).pin_memory(); pp.numpy()[:] = evp
         pe = torch.empty(len(ev), dtype=torch.int32).pin_memory(); pe.numpy().view(np.uint32)[:] = ev

@@ -623,6 +623,7 @@ struct qb_pipeline {
     uint32_t *synZ = nullptr, *synX = nullptr, *trueZ = nullptr, *trueX = nullptr, *hardZ = nullptr, *hardX = nullptr;
     uint8_t *convZ = nullptr, *convX = nullptr, *flags = nullptr;
     int32_t *itZ = nullptr, *itX = nullptr, *failZ = nullptr, *failX = nullptr, *nfail = nullptr;   // nfail[2]
+    int32_t *fwZ = nullptr, *fwX = nullptr, *sortZ = nullptr, *sortX = nullptr;   // failure weights / weight-sorted queues
     float *postZ = nullptr, *postX = nullptr;
     int64_t *counts = nullptr;   // device [8]
     int32_t *ev_ptr = nullptr; uint32_t *events = nullptr; size_t ev_cap = 0;
@@ -678,7 +679,7 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
         a.damping = 1.0f; a.clip = cfg->clip_llr; a.dense_variant = 0;
         a.hard_bits = side ? p->hardX : p->hardZ; a.converged = side ? p->convX : p->convZ;
         a.final_iter = side ? p->itX : p->itZ; a.post = side ? p->postX : p->postZ; a.post_failed_only = 1;
-        a.fail_count = p->nfail + side; a.fail_idx = side ? p->failX : p->failZ;
+        a.fail_count = p->nfail + side; a.fail_idx = side ? p->failX : p->failZ; a.fail_wt = side ? p->fwX : p->fwZ;
         if (int rc = launch_minsum(d, a, st)) return rc;
         p->stats.kernel_launches++;
     }
@@ -686,9 +687,12 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
     if (cfg->use_osd) {
         for (int side = 0; side < 2; ++side) {
             qb_decoder *d = side ? p->dx : p->dz;
+            if (int rc = launch_sort_failures(side ? p->failX : p->failZ, side ? p->fwX : p->fwZ, p->nfail + side,
+                                              side ? p->sortX : p->sortZ, st)) return rc;
+            p->stats.kernel_launches++;
             OsdLaunch a{};
             a.syn_bits = side ? p->synX : p->synZ; a.hard_bits = side ? p->hardX : p->hardZ;
-            a.post = side ? p->postX : p->postZ; a.fail_idx = side ? p->failX : p->failZ;
+            a.post = side ? p->postX : p->postZ; a.fail_idx = side ? p->sortX : p->sortZ;
             a.F = B; a.n_fail_d = p->nfail + side;
             if (int rc = launch_osd0(d, a, st)) return rc;
             p->stats.kernel_launches++;
@@ -751,6 +755,7 @@ int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_
 #define AL(ptr, cnt) if (!rc) rc = dalloc(p, &p->ptr, cnt);
     AL(synZ, B * gz.mw) AL(synX, B * gx.mw) AL(trueZ, B) AL(trueX, B) AL(hardZ, B * gz.nw) AL(hardX, B * gx.nw)
     AL(convZ, B) AL(convX, B) AL(flags, B) AL(itZ, B) AL(itX, B) AL(failZ, B) AL(failX, B) AL(nfail, 2)
+    AL(fwZ, B) AL(fwX, B) AL(sortZ, B) AL(sortX, B)
     AL(postZ, B * gz.n) AL(postX, B * gx.n) AL(counts, 8) AL(ev_ptr, B + 1) AL(syn8, B * std::max(gz.m, gx.m))
 #undef AL
     if (!rc) {

@@ -116,6 +116,7 @@ struct MinsumLaunch {
     int post_failed_only;       // write post only for non-converged shots
     int32_t *fail_count;        // nullable: device counter, non-converged shots are appended
     int32_t *fail_idx;
+    int32_t *fail_wt;           // nullable: residual syndrome weight of each appended shot (OSD scheduling hint)
 };
 int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st);
 int upload_alpha(qb_decoder *dec, int max_iter, int alpha_mode, double alpha, const double *seq, int len,
@@ -134,6 +135,8 @@ struct OsdLaunch {
     int exact_rows;             // emulate the reference's pivot-row order (inconsistent syndromes)
 };
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
+// order the failure queue by descending residual weight (longest elimination first)
+int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail_d, int32_t *sorted_idx, cudaStream_t st);
 
 int launch_events_syndrome(qb_sampler *s, const int32_t *ev_ptr_d, const uint32_t *events_d, int B,
                            uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX, cudaStream_t st);

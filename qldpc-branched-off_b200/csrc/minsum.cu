@@ -191,6 +191,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
     int *s_rdeg = s_cptr + g.n_cslices;                                              // degree | exact-path flag << 8
     int *s_cdeg = s_rdeg + g.n_rslices;
     __shared__ int s_unsat[S];
+    __shared__ int s_wt[S];
     __shared__ int s_active[S];
     __shared__ int s_nactive;
 
@@ -217,7 +218,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
             syn[i] = (shot0 + s < a.B) ? a.syn_bits[(size_t)(shot0 + s) * g.mw + w] : 0u;
             par[i] = 0u;
         }
-        if (tid < S) { s_active[tid] = (shot0 + tid < a.B); s_unsat[tid] = 0; }
+        if (tid < S) { s_active[tid] = (shot0 + tid < a.B); s_unsat[tid] = 0; s_wt[tid] = 0; }
         if (tid == 0) s_nactive = min(S, a.B - shot0);
         __syncthreads();
         if (a.max_iter <= 0) {
@@ -229,7 +230,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                 if (a.post) for (int j = tid; j < g.n; j += blockDim.x) a.post[shot * g.n + j] = 0.f;
                 if (tid == 0) {
                     a.converged[shot] = 0; a.final_iter[shot] = -1;
-                    if (a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = (int)shot;
+                    if (a.fail_count) { const int slot = atomicAdd(a.fail_count, 1); a.fail_idx[slot] = (int)shot; if (a.fail_wt) a.fail_wt[slot] = 0; }
                 }
             }
             __syncthreads();
@@ -322,7 +323,8 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
 
             // ---- convergence: H.hard == syndrome  (kernels.py:352-364) ---------------------------
             for (int i = tid; i < S * g.mw; i += blockDim.x) {
-                if (par[i] != syn[i]) s_unsat[i / g.mw] = 1;
+                const uint32_t d = par[i] ^ syn[i];
+                if (d) { s_unsat[i / g.mw] = 1; atomicAdd(&s_wt[i / g.mw], __popc(d)); }    // weight of the residual syndrome
                 par[i] = 0u;
             }
             __syncthreads();
@@ -344,7 +346,11 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                     if (tid == 0) {
                         a.converged[shot] = conv ? 1 : 0;
                         a.final_iter[shot] = it;
-                        if (!conv && a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = (int)shot;
+                        if (!conv && a.fail_count) {
+                            const int slot = atomicAdd(a.fail_count, 1);
+                            a.fail_idx[slot] = (int)shot;
+                            if (a.fail_wt) a.fail_wt[slot] = s_wt[s];
+                        }
                     }
                 }
             }
@@ -360,7 +366,7 @@ minsum_fast_kernel(GraphDev g, MinsumLaunch a)
                 }
             }
             __syncthreads();
-            if (tid < S) s_unsat[tid] = 0;
+            if (tid < S) { s_unsat[tid] = 0; s_wt[tid] = 0; }
             if (s_nactive == 0) break;
             // a finished shot keeps being iterated (its outputs are already written and never
             // overwritten: s_active gates the output stage), which keeps the inner loops branch-free.
@@ -451,7 +457,7 @@ minsum_general_kernel(GraphDev g, MinsumLaunch a, float *ws)
         if (tid == 0) {
             a.converged[shot] = conv ? 1 : 0;
             a.final_iter[shot] = fin;
-            if (!conv && a.fail_count) a.fail_idx[atomicAdd(a.fail_count, 1)] = shot;
+            if (!conv && a.fail_count) { const int slot = atomicAdd(a.fail_count, 1); a.fail_idx[slot] = shot; if (a.fail_wt) a.fail_wt[slot] = 0; }
         }
         __syncthreads();
     }

@@ -525,6 +525,29 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     return QB_OK;
 }
 
+// Counting sort of the failure queue by residual-syndrome weight, heaviest first: the number of pivots an
+// OSD-0 needs grows with that weight, so the dynamic work distribution starts the long eliminations first.
+__global__ void __launch_bounds__(1024) sort_failures_kernel(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail,
+                                                             int32_t *sorted_idx)
+{
+    __shared__ int hist[256], start[256];
+    const int tid = threadIdx.x, F = *n_fail;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < F; i += blockDim.x) atomicAdd(&hist[255 - min(255, max(0, fail_wt[i] >> 1))], 1);
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int b = 0; b < 256; ++b) { start[b] = run; run += hist[b]; } }
+    __syncthreads();
+    for (int i = tid; i < F; i += blockDim.x) sorted_idx[atomicAdd(&start[255 - min(255, max(0, fail_wt[i] >> 1))], 1)] = fail_idx[i];
+}
+
+int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail_d, int32_t *sorted_idx, cudaStream_t st)
+{
+    sort_failures_kernel<<<1, 1024, 0, st>>>(fail_idx, fail_wt, n_fail_d, sorted_idx);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
 {
     if (a.F <= 0) return QB_OK;

@@ -65,7 +65,7 @@ def _dist():
 class ShotEngine:
     """Device state of one (code, p): sampler, two decoders, pipeline."""
 
-    def __init__(self, compiled, Lx, Lz, matrices, max_batch=16384, device=None):
+    def __init__(self, compiled, Lx, Lz, matrices, max_batch=65536, device=None):
         ft = fault_tables_for(compiled, Lx, Lz)
         self.ft = ft
         k = np.asarray(Lx).shape[0]
@@ -166,7 +166,7 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
 
     dist, rank, world = _dist()
     if batch_size is None:
-        batch_size = int(min(16384, max(256, -(-max_trials // world))))
+        batch_size = int(min(65536, max(256, -(-max_trials // world))))
     eng = ShotEngine(compiled, Lx, Lz, matrices, max_batch=batch_size)
     cfg = _lib.make_config(maxIter, qmode, alpha_z, alpha_x, clip_llr=20.0, use_osd=True)
     try:
