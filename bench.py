@@ -63,6 +63,11 @@ def summarize_clocks(lines):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one minsum_fast_kernel launch, from the `ncu --set full` capture of
+# this command (profiles/r1_ncu_full_final_summary.txt): 0.0216 GB + 2.2022 GB for a 65536-shot launch.
+NCU_TRAFFIC_BYTES = {65536: 2.2238e9}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -268,7 +273,8 @@ def main():
                        "sampler": "Philox4x32-10 on device, counter = global shot index",
                        "l2": "no flush needed: per-batch posterior/state buffers (>1 GB) exceed the 126 MB L2 and every step decodes new shots"},
             "roofline": {"bound": "hbm", "kernel": "minsum_fast_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(shots_per_launch), "traffic_unit": "bytes/launch (ncu, profiles/)",
+                         "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
                          "ms_per_launch": ms_launch, "shots_per_launch": shots_per_launch,
                          "note": "HBM is not the binding resource by design (messages stay in shared memory); see roofline_smem"},
             "roofline_smem": {"bound": "smem", "kernel": "minsum_fast_kernel", "edge_messages_per_s": em_per_s,
