@@ -114,7 +114,10 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
                         } else {
                             qb = __float_as_uint(q);
                         }
-                        const float ab = fminf(fabsf(q), clip);                // |clip(q)|, kernels.py:330-333
+                        // clip(q) (kernels.py:330-333) is monotone in |q| and keeps the sign, so the two smallest
+                        // |clip(q)| are min(., clip) of the two smallest |q|: the clamp is applied once per row below
+                        // (rows of degree 1 keep min2 = +inf, so the EXACT variant clamps per edge like the reference)
+                        const float ab = EXACT ? fminf(fabsf(q), clip) : fabsf(q);
                         nsc[s] = __funnelshift_l(qb, nsc[s], 1);
                         uint32_t lt;                                           // sign bit set iff ab < min1 (strict: first minimum wins)
                         if constexpr (EXACT) lt = (ab < mn1[s]) ? 0x80000000u : 0u;
@@ -144,8 +147,8 @@ __device__ __forceinline__ void row_slice(const float *vals, uint4 *chk, const u
             const uint32_t tot = (sbit ^ (uint32_t)(__popc(nz[s]) + __popc(nw_[s]))) & 1u;
             const uint32_t tmask = 0u - tot;
             uint4 st;
-            st.x = __float_as_uint(alpha * mn1[s]);
-            st.y = __float_as_uint(alpha * mn2[s]);
+            st.x = __float_as_uint(alpha * (EXACT ? mn1[s] : fminf(mn1[s], clip)));
+            st.y = __float_as_uint(alpha * (EXACT ? mn2[s] : fminf(mn2[s], clip)));
             st.z = nz[s] ^ tmask;
             st.w = ((nw_[s] ^ tmask) & 0x00FFFFFFu) | ((uint32_t)am[s] << 24);
             chk[s * crow + r] = st;
