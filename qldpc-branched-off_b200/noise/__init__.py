@@ -10,4 +10,8 @@ def __getattr__(name):          # lazy: importing the package must not require t
     if name in ("run_trial_fast", "run_trials_from_events", "events_from_random"):
         from . import simulation
         return getattr(simulation, name)
+    if name in ("simulate_circuit_Z", "simulate_circuit_X", "sparsify_syndrome", "extract_data_qubit_state",
+                "generate_noisy_circuit"):
+        from . import twins
+        return getattr(twins, name)
     raise AttributeError(name)

@@ -147,3 +147,37 @@ def test_install_as_src_aliases_reference_module_names():
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_host_twins_agree_with_table_builder():
+    """The tuple-circuit twins (reference simulation.py:114-229) and the bit-parallel builder describe the same
+    physics: a single inserted fault reproduces its decoding-matrix column and logical mask."""
+    from qldpc_b200.noise import simulate_circuit_Z, simulate_circuit_X, sparsify_syndrome, extract_data_qubit_state
+    s = code_setup("72"); cb, ft = s["cb"], s["ft"]
+    base, suffix = cb.get_full_circuit(), cb.cycle * 2
+    rng = np.random.default_rng(0)
+    for side, sim, checks, L, tab in (("Z", simulate_circuit_Z, cb.Xchecks, s["Lx"], ft.Z), ("X", simulate_circuit_X, cb.Zchecks, s["Lz"], ft.X)):
+        for f in rng.choice(len(tab.fault_loc), 12, replace=False):
+            loc, var = int(tab.fault_loc[f]), int(tab.fault_variant[f])
+            gate = base[loc]
+            p = side
+            err = (p, gate[1]) if var == 1 else ((p, gate[2]) if var == 2 else (p + p, gate[1], gate[2]))
+            pos = loc if gate[0].startswith("Meas") else loc + 1
+            circ = base[:pos] + [err] + base[pos:] + suffix
+            hist, state, smap, _ = sim(circ, cb.lin_order, cb.n, checks)
+            syn = sparsify_syndrome(hist, smap, checks)
+            col = int(tab.fault_col[f])
+            rows = tab.col_rows[tab.col_ptr[col]:tab.col_ptr[col + 1]]
+            assert np.array_equal(np.nonzero(syn)[0], rows)
+            logical = (np.asarray(L) @ extract_data_qubit_state(state, cb.lin_order, cb.data_qubits)) % 2
+            mask = sum(int(b) << i for i, b in enumerate(logical))
+            assert mask == int(tab.col_logmask[col])
+
+
+def test_plotting_shim_returns_reference_r2():
+    from qldpc_b200.utils.plotting import plot_alpha_comparison, plot_alpha_linearity, plot_simulation_results
+    res = {"72": {0.005: {"logical_error_rate": 0.3, "alpha_values_z": [0.4, 0.5, 0.6], "alpha_values_x": [0.3, 0.6, 0.5]}}}
+    r2 = plot_alpha_linearity(res, "/tmp/_qb_lin.png")
+    assert abs(r2["72"][0.005]["z"] - 1.0) < 1e-12 and 0 < r2["72"][0.005]["x"] < 1
+    plot_alpha_comparison(res, "/tmp/_qb_cmp.png")
+    plot_simulation_results({"72": {0.004: {"logical_error_rate": 0.1}, 0.006: {"logical_error_rate": 0.4}}}, "/tmp/_qb_res.png")
