@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "minsum.cu", "osd.cu", "sampler.cu"]
+SOURCES = ["api.cu", "minsum.cu", "minsum_edge.cu", "edge_layout.cu", "osd.cu", "sampler.cu"]
 OUT = os.path.join(HERE, "libqldpc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -223,6 +223,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
       if (!rc) { rc = to_device(d->owned, cdeg, &p8); g.cslice_deg = p8; } }
     if (!rc && !colsig.empty()) { rc = to_device(d->owned, colsig, &p16); g.colsig = reinterpret_cast<const uint4 *>(p16); }
 #undef UP
+    if (!rc && !g.nan_anywhere) rc = edge_plan_create(d, pf.data(), &d->edge);
     if (rc) { qb_decoder_destroy(d); return rc; }
     *out = d;
     return QB_OK;
@@ -236,6 +237,13 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     dec->g.nan_anywhere = dec->graph_nan;
     for (int j = 0; j < dec->g.n; ++j) { pf[j] = (float)prior[j]; if (!std::isfinite(prior[j])) dec->g.nan_anywhere = 1; }
     if (dec->g.n) QB_CUDA(cudaMemcpy(dec->d_prior, pf.data(), sizeof(float) * pf.size(), cudaMemcpyHostToDevice));
+    // the per-edge layout groups variables by prior value: rebuild it
+    QB_CUDA(cudaDeviceSynchronize());
+    edge_plan_destroy(dec->edge);
+    dec->edge = nullptr;
+    bool finite = true;
+    for (float v : pf) if (!std::isfinite(v)) finite = false;
+    if (finite) return edge_plan_create(dec, pf.data(), &dec->edge);
     return QB_OK;
 }
 
@@ -244,6 +252,7 @@ void qb_decoder_destroy(qb_decoder *dec)
     if (!dec) return;
     cudaSetDevice(dec->device);
     for (void *p : dec->owned) cudaFree(p);
+    edge_plan_destroy(dec->edge);
     if (dec->d_alpha) cudaFree(dec->d_alpha);
     dec->scratch.release(); dec->work.release();
     delete dec;

@@ -67,6 +67,7 @@ struct GraphDev {
     const uint32_t *logmask;                   // per column: bit b = logical row b contains the column
 };
 
+struct EdgePlan;   // per-edge min-sum kernel: layout + device tables (minsum_edge.cu)
 }  // namespace qb
 
 struct qb_decoder {
@@ -84,6 +85,7 @@ struct qb_decoder {
     qb::Scratch work;           // kernel workspaces (general min-sum messages, OSD spill)
     int sm_count = 148;
     int max_smem_optin = 0;
+    qb::EdgePlan *edge = nullptr;   // nullptr: graph does not fit the per-edge kernel
 };
 
 struct qb_sampler {
@@ -119,6 +121,9 @@ struct MinsumLaunch {
     int32_t *fail_wt;           // nullable: residual syndrome weight of each appended shot (OSD scheduling hint)
 };
 int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st);
+int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out);
+void edge_plan_destroy(EdgePlan *p);
+int launch_minsum_edge(qb_decoder *dec, EdgePlan *p, const MinsumLaunch &a, cudaStream_t st);
 int upload_alpha(qb_decoder *dec, int max_iter, int alpha_mode, double alpha, const double *seq, int len,
                  cudaStream_t st);
 

@@ -680,6 +680,7 @@ static int launch_fast(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
 int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
 {
     if (a.B <= 0) return QB_OK;
+    if (a.damping == 1.0f && dec->edge && a.max_iter > 0) return launch_minsum_edge(dec, dec->edge, a, st);
     const int S = (a.damping == 1.0f) ? fast_shots_per_cta(dec) : 0;
     if (S == 4) return launch_fast<4>(dec, a, st);
     if (S == 2) return launch_fast<2>(dec, a, st);

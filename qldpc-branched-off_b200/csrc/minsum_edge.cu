@@ -1,0 +1,557 @@
+// K3 (fast path): flooding min-sum with one float per Tanner-graph edge resident in shared memory.
+//
+// Reference semantics: src/decoding/kernels.py:235-366 (minsum_decoder_full) with damping == 1, which is
+// every call the engine makes (engine.py:84-88).  One persistent CTA per SM decodes one shot at a time:
+//
+//   E[slot]  one float per edge, in the conflict-free row-major layout built by edge_layout.cu.
+//            Between phase B and phase A it holds the variable-to-check message Q (kernels.py:323-345),
+//            between phase A and phase B the check-to-variable message R (kernels.py:283-316).
+//   phase A  one lane per check row: stream the row's Q with LDS.128, keep them in registers, reduce
+//            (min1 with the sign product in ONE instruction: min.xorsign.abs; min2 with two FMNMX), then
+//            R = sign * alpha * (|Q| == min1 ? min2 : min1) written back in place (STS.128).  The value test
+//            replaces the reference's argmin position: when two edges tie for min1, min2 == min1.
+//   phase B  one lane per variable: gather its <= 16 R through precomputed 16-bit slot indices (bank
+//            conflict free by construction), sum in row order + prior (kernels.py:316-320), hard decision,
+//            Q = clip(v - R) (NaN -> 0 first, kernels.py:327-333) scattered back to the same slots.
+//            Convergence (H.hard == syndrome, kernels.py:352-364) is first tested on a 32-bit linear fingerprint
+//            (XOR of per-column random signatures over the variables whose hard decision is 1 against the
+//            XOR of per-row masks over the syndrome) and confirmed exactly only when the fingerprints agree,
+//            so the common non-converged iteration never walks the graph a second time.
+// Iteration 0 reads Q = prior (unclipped, kernels.py:263-265) straight from a global image of E.
+// No fast-math: IEEE inf/NaN conventions are the reference's (degree-1 rows send +-inf).
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "edge_layout.h"
+
+namespace qb {
+
+struct EdgeDev {
+    int n_rsl, n_csl, e_words, idx_words, nw, n, mw;
+    const float4 *E0;            // [e_words/4] prior per slot, +inf in unused slots
+    const uint32_t *col_idx;     // [idx_words]
+    const uint32_t *col_rowpos;  // [idx_words]
+    const uint2 *rtask;          // [n_rsl]
+    const uint2 *ctask;          // [n_csl]
+    const uint16_t *row_id;      // [n_rsl*32]
+    const uint2 *row_pads;       // [n_rsl*32] 4 x u16
+    const uint16_t *var_id;      // [n_csl*32]
+    const float *lane_prior;     // [n_csl*32] or nullptr (uniform priors in ctask)
+    const int32_t *wr_ptr, *wc_ptr;
+    const uint4 *wc_cls;         // [nwarps] 16 x u8 slices per class
+    const uint32_t *row_mask;    // [n_rsl*32]
+    const uint32_t *col_sig;     // [n_csl*32]
+};
+
+__device__ __forceinline__ float min_xorsign_abs(float a, float b)
+{
+    float d;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+// ---- phase A: one row slice, K chunks of 4 edges per lane held in registers -------------------------------
+template <int K, bool FIRST>
+__device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_unit, int stride, int lane,
+                                         uint32_t synsign, float alpha, uint2 pads)
+{
+    float4 q[K];
+    float4 *e4 = reinterpret_cast<float4 *>(E) + base_unit + lane;
+    if constexpr (FIRST) {
+        const float4 *g4 = E0 + base_unit + lane;
+#pragma unroll
+        for (int c = 0; c < K; ++c) q[c] = __ldg(g4 + c * stride);
+    } else {
+#pragma unroll
+        for (int c = 0; c < K; ++c) q[c] = e4[c * stride];
+    }
+    float m1s = INFINITY, m2 = INFINITY;                   // |m1s| = running minimum, sign(m1s) = running sign product
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const float v[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m2 = fminf(m2, fmaxf(fabsf(v[i]), fabsf(m1s)));
+            m1s = min_xorsign_abs(m1s, v[i]);
+        }
+    }
+    const float m1 = fabsf(m1s);
+    const uint32_t tot = (__float_as_uint(m1s) & 0x80000000u) ^ synsign;      // kernels.py:289-298
+    uint32_t a1 = __float_as_uint(alpha * m1) ^ tot;                           // kernels.py:309-314
+    uint32_t a2 = __float_as_uint(alpha * m2) ^ tot;
+    asm volatile("" : "+r"(a1), "+r"(a2));                  // keep the multiplications out of the per-edge code
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const float v[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t sel = (fabsf(v[i]) == m1) ? a2 : a1;
+            r[i] = __uint_as_float(sel ^ (__float_as_uint(v[i]) & 0x80000000u));
+        }
+        e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    // unused slots back to +inf (every row has at least one)
+    E[pads.x & 0xFFFFu] = INFINITY;
+    if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;
+    if ((pads.y & 0xFFFFu) != 0xFFFFu) E[pads.y & 0xFFFFu] = INFINITY;
+    if ((pads.y >> 16) != 0xFFFFu) E[pads.y >> 16] = INFINITY;
+}
+
+// generic row (K > 9): two passes over shared memory
+template <bool FIRST>
+__device__ __noinline__ void row_task_loop(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
+                                           uint32_t synsign, float alpha, uint2 pads)
+{
+    float4 *e4 = reinterpret_cast<float4 *>(E) + base_unit + lane;
+    const float4 *g4 = E0 + base_unit + lane;
+    float m1s = INFINITY, m2 = INFINITY;
+    for (int c = 0; c < K; ++c) {
+        const float4 qq = FIRST ? __ldg(g4 + c * stride) : e4[c * stride];
+        const float v[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m2 = fminf(m2, fmaxf(fabsf(v[i]), fabsf(m1s)));
+            m1s = min_xorsign_abs(m1s, v[i]);
+        }
+    }
+    const float m1 = fabsf(m1s);
+    const uint32_t tot = (__float_as_uint(m1s) & 0x80000000u) ^ synsign;
+    uint32_t a1 = __float_as_uint(alpha * m1) ^ tot, a2 = __float_as_uint(alpha * m2) ^ tot;
+    asm volatile("" : "+r"(a1), "+r"(a2));
+    for (int c = 0; c < K; ++c) {
+        const float4 qq = FIRST ? __ldg(g4 + c * stride) : e4[c * stride];
+        const float v[4] = {qq.x, qq.y, qq.z, qq.w};
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t sel = (fabsf(v[i]) == m1) ? a2 : a1;
+            r[i] = __uint_as_float(sel ^ (__float_as_uint(v[i]) & 0x80000000u));
+        }
+        e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    E[pads.x & 0xFFFFu] = INFINITY;
+    if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;
+    if ((pads.y & 0xFFFFu) != 0xFFFFu) E[pads.y & 0xFFFFu] = INFINITY;
+    if ((pads.y >> 16) != 0xFFFFu) E[pads.y >> 16] = INFINITY;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
+                                             uint32_t synsign, float alpha, uint2 pads)
+{
+    switch (K) {
+    case 1: row_task<1, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 2: row_task<2, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 3: row_task<3, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 4: row_task<4, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 5: row_task<5, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 6: row_task<6, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 7: row_task<7, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 8: row_task<8, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    case 9: row_task<9, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
+    default: row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, pads); break;
+    }
+}
+
+// ---- phase B ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v)); }
+
+// state shared by the column tasks of one warp during one phase B
+struct ColCtx {
+    const uint2 *desc;      // shared: task descriptors {idx word offset of lane 0, prior}
+    const uint32_t *idx;    // shared: slot indices (absolute shared word addresses, see the staging loop), + lane
+    int t;                  // next task
+    float clip;
+    const uint32_t *sig;    // fingerprint table + lane
+    uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
+    uint32_t *hperm;        // hard-decision words
+    const uint16_t *vid;    // variable ids + lane (posterior output)
+    float *post;            // posterior row of the shot
+    bool lane0;
+};
+
+// one full slice (32 variables) of degree D with a uniform prior
+template <int D, bool EXACT, bool WRITE_V>
+__device__ __forceinline__ void col_task(ColCtx &c)
+{
+    const uint2 d = c.desc[c.t];
+    const uint32_t *ix = c.idx + d.x;
+    uint32_t w[(D + 1) / 2 + 1];
+#pragma unroll
+    for (int kk = 0; kk < (D + 1) / 2; ++kk) w[kk] = ix[kk * 32];
+    uint32_t addr[D + 1];
+    float r[D + 1];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        addr[k] = (k & 1) ? ((w[k >> 1] >> 14) & 0x3FFFCu) : ((w[k >> 1] << 2) & 0x3FFFCu);
+        r[k] = lds_f32(addr[k]);
+    }
+    float acc = D > 0 ? r[0] : 0.f;                        // kernels.py:316 (row order)
+#pragma unroll
+    for (int k = 1; k < D; ++k) acc += r[k];
+    const float v = acc + __uint_as_float(d.y);            // kernels.py:320
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        float q = v - r[k];                                // kernels.py:326
+        if constexpr (EXACT) q = (q != q) ? 0.f : q;       // kernels.py:328-329
+        sts_f32(addr[k], fminf(fmaxf(q, -c.clip), c.clip));   // kernels.py:330-333
+    }
+    const bool neg = v < 0.f;                              // kernels.py:349
+    if (neg) c.fp ^= __ldg(c.sig + c.t * 32);
+    const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
+    if (c.lane0) c.hperm[c.t] = hw;
+    if constexpr (WRITE_V) c.post[c.vid[c.t * 32]] = v;
+    c.t += 1;
+}
+
+// any slice: partial, per-lane priors, large degree.  Returns the fingerprint contribution of the lane.
+template <bool WRITE_V>
+__device__ __noinline__ uint32_t col_task_generic(float *E, const uint32_t *idx /* global copy: E-relative slots */, uint2 gd, const float *lane_prior, int lane, float clip,
+                                                  const uint32_t *sig, uint32_t *hperm, const uint16_t *vid, float *post)
+{
+    const int D = (gd.x >> 16) & 63, nl = (gd.x >> 22) & 63;
+    const uint32_t *ix = idx + (gd.x & 0xFFFFu) * 32 + lane;
+    bool neg = false;
+    uint32_t fp = 0u;
+    if (lane < nl) {
+        float acc = 0.f;
+        for (int k = 0; k < D; ++k) {
+            const uint32_t w = ix[(k >> 1) * 32];
+            acc += E[(k & 1) ? (w >> 16) : (w & 0xFFFFu)];
+        }
+        const float v = acc + (lane_prior ? lane_prior[lane] : __uint_as_float(gd.y));
+        for (int k = 0; k < D; ++k) {
+            const uint32_t w = ix[(k >> 1) * 32];
+            const uint32_t s = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+            float q = v - E[s];
+            q = (q != q) ? 0.f : q;
+            E[s] = fminf(fmaxf(q, -clip), clip);
+        }
+        neg = v < 0.f;
+        if (neg) fp = __ldg(sig);
+        if (WRITE_V) post[*vid] = v;
+    }
+    const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
+    if (lane == 0) *hperm = hw;
+    return fp;
+}
+
+template <int D, bool EXACT, bool WRITE_V>
+__device__ __forceinline__ void col_class(ColCtx &c, int cnt)
+{
+    for (int i = 0; i < cnt; ++i) col_task<D, EXACT, WRITE_V>(c);
+}
+
+template <bool WRITE_V>
+__device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, float *E, const uint32_t *gidx, const uint2 *gtask,
+                                        const float *lane_prior, int t0, int lane)
+{
+    col_class<0, false, WRITE_V>(c, cls.x & 255);
+    col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255);
+    col_class<2, false, WRITE_V>(c, (cls.x >> 16) & 255);
+    col_class<3, false, WRITE_V>(c, cls.x >> 24);
+    col_class<4, false, WRITE_V>(c, cls.y & 255);
+    col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255);
+    col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255);
+    col_class<7, false, WRITE_V>(c, cls.y >> 24);
+    col_class<8, false, WRITE_V>(c, cls.z & 255);
+    col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255);
+    col_class<2, true, WRITE_V>(c, (cls.z >> 16) & 255);
+    col_class<3, true, WRITE_V>(c, cls.z >> 24);
+    col_class<4, true, WRITE_V>(c, cls.w & 255);
+    col_class<5, true, WRITE_V>(c, (cls.w >> 8) & 255);
+    col_class<6, true, WRITE_V>(c, (cls.w >> 16) & 255);
+    const int ngen = cls.w >> 24;
+    if (ngen) {
+        int t = t0 + (int)((cls.x & 255) + ((cls.x >> 8) & 255) + ((cls.x >> 16) & 255) + (cls.x >> 24) + (cls.y & 255) + ((cls.y >> 8) & 255) +
+                           ((cls.y >> 16) & 255) + (cls.y >> 24) + (cls.z & 255) + ((cls.z >> 8) & 255) + ((cls.z >> 16) & 255) + (cls.z >> 24) +
+                           (cls.w & 255) + ((cls.w >> 8) & 255) + ((cls.w >> 16) & 255));
+        for (int i = 0; i < ngen; ++i, ++t) {
+            c.fp ^= col_task_generic<WRITE_V>(E, gidx, __ldg(&gtask[t]), lane_prior ? lane_prior + t * 32 : nullptr, lane, c.clip,
+                                              c.sig + t * 32, c.hperm + t, c.vid + t * 32, c.post);
+        }
+    }
+}
+
+// weight of the residual syndrome par ^ syn (0 = converged); resets par.  Called by warp 0 only.
+__device__ __forceinline__ int residual_weight(uint32_t *par, const uint32_t *syn, int n_rsl, int lane)
+{
+    int wt = 0;
+    for (int w = lane; w < n_rsl; w += 32) { wt += __popc(par[w] ^ syn[w]); par[w] = 0u; }
+    return __reduce_add_sync(0xFFFFFFFFu, wt);
+}
+
+// exact H.hard for the hard decision in hperm: par ^= rows of every variable whose bit is set (all threads; par must be 0)
+__device__ __forceinline__ void parity_of_hard(const EdgeDev &eg, const uint32_t *hperm, uint32_t *par, int tid, int nthreads)
+{
+    for (int t = tid; t < eg.n_csl; t += nthreads) {
+        uint32_t bits = hperm[t];
+        if (!bits) continue;
+        const uint32_t dx = __ldg(&eg.ctask[t]).x;
+        const int D = (dx >> 16) & 63;
+        const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            for (int k = 0; k < D; ++k) {
+                const uint32_t w = __ldg(&rp[(k >> 1) * 32 + b]);
+                const uint32_t pos = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+                atomicXor(&par[pos >> 5], 1u << (pos & 31));
+            }
+        }
+    }
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *E = reinterpret_cast<float *>(smem_raw);                                   // [e_words]
+    uint32_t *idx = reinterpret_cast<uint32_t *>(E + eg.e_words);                     // [idx_words]
+    uint2 *ctask = reinterpret_cast<uint2 *>(idx + eg.idx_words);                     // [n_csl] {idx address, prior}
+    uint2 *rtask = ctask + eg.n_csl;                                                  // [n_rsl]
+    uint32_t *syn = reinterpret_cast<uint32_t *>(rtask + eg.n_rsl);                   // [n_rsl] permuted syndrome bits
+    uint32_t *par = syn + eg.n_rsl;                                                   // [n_rsl] parity of the hard decision
+    uint32_t *hperm = par + eg.n_rsl;                                                 // [n_csl] hard decision, slice order
+    uint32_t *hnat = hperm + eg.n_csl;                                                // [nw] hard decision, natural order
+    __shared__ int s_wt, s_next;
+    __shared__ uint32_t s_fp[2], s_target;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // slot indices become absolute shared word addresses (E base folded in), so that a gather address is one
+    // shift + one mask away from the packed pair
+    const uint32_t e_word = (uint32_t)__cvta_generic_to_shared(E) >> 2;
+    for (int i = tid; i < eg.idx_words; i += THREADS) idx[i] = eg.col_idx[i] + (e_word | (e_word << 16));
+    for (int i = tid; i < eg.n_csl; i += THREADS) {
+        const uint2 d = eg.ctask[i];
+        ctask[i] = make_uint2((d.x & 0xFFFFu) * 32u, d.y);
+    }
+    for (int i = tid; i < eg.n_rsl; i += THREADS) rtask[i] = eg.rtask[i];
+    const int r0 = eg.wr_ptr[warp], r1 = eg.wr_ptr[warp + 1];
+    const int c0 = eg.wc_ptr[warp];
+    const uint4 cls = eg.wc_cls[warp];
+    if (tid == 0) { s_next = atomicAdd(shot_counter, 1); s_fp[0] = 0u; s_fp[1] = 0u; s_target = 0u; }
+    __syncthreads();
+    int shot = s_next;
+    const bool api = !a.post_failed_only;
+
+    while (shot < a.B) {                                                              // uniform
+        // ---- load: permuted syndrome words and their fingerprint, parity = 0 ----------------------------------
+        {
+            uint32_t tg = 0u;
+            for (int t = warp; t < eg.n_rsl; t += THREADS / 32) {
+                const uint32_t rid = eg.row_id[t * 32 + lane];
+                const bool bit = rid != 0xFFFFu && ((a.syn_bits[(size_t)shot * eg.mw + (rid >> 5)] >> (rid & 31)) & 1u);
+                if (bit) tg ^= eg.row_mask[t * 32 + lane];
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+                if (lane == 0) { syn[t] = word; par[t] = 0u; }
+            }
+            tg = __reduce_xor_sync(0xFFFFFFFFu, tg);
+            if (lane == 0 && tg) atomicXor(&s_target, tg);
+        }
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(shot_counter, 1);                            // prefetch the next shot id
+        const uint32_t target = s_target;
+
+        bool conv = false;
+        int fin = a.max_iter - 1, wt = 0;
+        for (int it = 0; it < a.max_iter; ++it) {
+            // ---- phase A --------------------------------------------------------------------------------
+            const float alpha = a.alpha_d[it];
+            for (int t = r0; t < r1; ++t) {
+                const uint2 d = rtask[t];
+                const int K = d.y & 255, nl = (d.y >> 8) & 255, stride = d.y >> 16;
+                if (K == 0 || lane >= nl) continue;
+                const uint32_t synsign = ((syn[t] >> lane) & 1u) << 31;
+                const uint2 pads = __ldg(&eg.row_pads[t * 32 + lane]);
+                if (it == 0) row_dispatch<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, pads);
+                else row_dispatch<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, pads);
+            }
+            if (tid == 0) s_fp[it & 1] = 0u;                                           // fingerprint accumulator of this iteration
+            __syncthreads();
+            // ---- phase B --------------------------------------------------------------------------------
+            ColCtx c;
+            c.desc = ctask;
+            c.idx = idx + lane;
+            c.t = c0;
+            c.clip = a.clip;
+            c.sig = eg.col_sig + lane;
+            c.fp = 0u;
+            c.hperm = hperm;
+            c.vid = eg.var_id + lane;
+            c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
+            c.lane0 = lane == 0;
+            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane);
+            else phase_b<false>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane);
+            const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp);
+            if (lane == 0 && fp) atomicXor(&s_fp[it & 1], fp);
+            __syncthreads();
+            // ---- convergence: fingerprint of H.hard against the syndrome's, exact test only on a match -----
+            if (s_fp[it & 1] == target) {                                              // uniform
+                parity_of_hard(eg, hperm, par, tid, THREADS);
+                __syncthreads();
+                if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
+                __syncthreads();
+                if (s_wt == 0) { conv = true; fin = it; break; }                       // kernels.py:352-364
+            }
+        }
+        if (!conv && a.max_iter > 0 && a.fail_wt) {                                    // weight of the residual syndrome (OSD scheduling hint)
+            parity_of_hard(eg, hperm, par, tid, THREADS);
+            __syncthreads();
+            if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
+            __syncthreads();
+            wt = s_wt;
+        }
+        // ---- output: hard decision back to natural column order ------------------------------------------
+        for (int w = tid; w < eg.nw; w += THREADS) hnat[w] = 0u;
+        if (tid == 0) s_target = 0u;
+        __syncthreads();
+        for (int t = tid; t < eg.n_csl; t += THREADS) {
+            uint32_t bits = hperm[t];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t vid = eg.var_id[t * 32 + b];
+                atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
+            }
+        }
+        __syncthreads();
+        for (int w = tid; w < eg.nw; w += THREADS) a.hard_bits[(size_t)shot * eg.nw + w] = hnat[w];
+        if (tid == 0) {
+            a.converged[shot] = conv ? 1 : 0;
+            a.final_iter[shot] = fin;
+            if (!conv && a.fail_count) {
+                const int slot = atomicAdd(a.fail_count, 1);
+                a.fail_idx[slot] = shot;
+                if (a.fail_wt) a.fail_wt[slot] = wt;
+            }
+        }
+        shot = s_next;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct EdgePlan {
+    EdgeLayout L;
+    EdgeDev dev{};
+    std::vector<void *> owned;
+    float *d_E0 = nullptr;
+    float *d_lane_prior = nullptr;
+    int *d_counter = nullptr;
+    int threads = 0, ctas_per_sm = 0;
+    size_t smem = 0;
+};
+
+static size_t edge_smem_bytes(const EdgeLayout &L, int nw)
+{
+    return (size_t)L.e_words * 4 + (size_t)L.idx_words * 4 + (size_t)L.n_csl * 8 + (size_t)L.n_rsl * 8 +
+           (size_t)L.n_rsl * 8 + (size_t)L.n_csl * 4 + (size_t)nw * 4 + 64;
+}
+
+template <class T>
+static int up(EdgePlan *p, const std::vector<T> &h, const T **out)
+{
+    T *d = nullptr;
+    QB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), sizeof(T) * std::max<size_t>(1, h.size())));
+    p->owned.push_back(d);
+    if (!h.empty()) QB_CUDA(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    *out = d;
+    return QB_OK;
+}
+
+void edge_plan_destroy(EdgePlan *p)
+{
+    if (!p) return;
+    for (void *q : p->owned) cudaFree(q);
+    delete p;
+}
+
+static std::vector<float> edge_E0(const EdgeLayout &L, const float *prior)
+{
+    std::vector<float> e0(L.e_words, INFINITY);
+    for (int i = 0; i < L.e_words; ++i) if (L.slot_var[i] >= 0) e0[i] = prior[L.slot_var[i]] + 0.0f;   // -0.0 -> +0.0
+    return e0;
+}
+
+// Build (or rebuild after a prior change) the per-edge plan of a decoder.  *out = nullptr when the graph
+// does not fit the kernel (the caller falls back to the compressed-state kernel).
+int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out)
+{
+    *out = nullptr;
+    if (getenv("QLDPC_B200_NO_EDGE")) return QB_OK;
+    const GraphDev &g = dec->g;
+    if (g.m <= 0 || g.n <= 0 || g.nnz <= 0) return QB_OK;
+    const size_t limit = (size_t)dec->max_smem_optin;
+    int nwarps = 32;
+    EdgeLayout L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
+    if (!L.ok) return QB_OK;
+    size_t smem = edge_smem_bytes(L, g.nw);
+    if (smem > limit) return QB_OK;
+    // several CTAs per SM for small codes: fewer warps each
+    int ctas = (int)std::min<size_t>(4, (limit + 1024) / (smem + 1024));
+    if (const char *e = getenv("QLDPC_B200_EDGE_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));
+    int want = ctas >= 4 ? 8 : (ctas >= 2 ? 16 : 32);
+    if (const char *e = getenv("QLDPC_B200_EDGE_WARPS")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) want = w; }
+    if (want != nwarps) {
+        nwarps = want;
+        L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
+        if (!L.ok) return QB_OK;
+        smem = edge_smem_bytes(L, g.nw);
+        if (smem > limit) return QB_OK;
+    }
+    EdgePlan *p = new EdgePlan();
+    p->threads = nwarps * 32; p->ctas_per_sm = ctas; p->smem = smem;
+    EdgeDev &d = p->dev;
+    d.n_rsl = L.n_rsl; d.n_csl = L.n_csl; d.e_words = L.e_words; d.idx_words = L.idx_words;
+    d.nw = g.nw; d.n = g.n; d.mw = g.mw;
+    int rc = QB_OK;
+    const std::vector<float> e0 = edge_E0(L, prior_h);
+    const float *pf = nullptr; const uint32_t *pu = nullptr; const uint16_t *ph = nullptr; const int32_t *pi = nullptr;
+    if (!rc) { rc = up(p, e0, &pf); d.E0 = reinterpret_cast<const float4 *>(pf); p->d_E0 = const_cast<float *>(pf); }
+    if (!rc) { rc = up(p, L.col_idx, &pu); d.col_idx = pu; }
+    if (!rc) { rc = up(p, L.col_rowpos, &pu); d.col_rowpos = pu; }
+    if (!rc) { rc = up(p, L.rtask, &pu); d.rtask = reinterpret_cast<const uint2 *>(pu); }
+    if (!rc) { rc = up(p, L.ctask, &pu); d.ctask = reinterpret_cast<const uint2 *>(pu); }
+    if (!rc) { rc = up(p, L.row_id, &ph); d.row_id = ph; }
+    if (!rc) { rc = up(p, L.row_pads, &ph); d.row_pads = reinterpret_cast<const uint2 *>(ph); }
+    if (!rc) { rc = up(p, L.var_id, &ph); d.var_id = ph; }
+    d.lane_prior = nullptr;
+    if (!rc && !L.uniform_prior) { rc = up(p, L.lane_prior, &pf); d.lane_prior = pf; }
+    if (!rc) { rc = up(p, L.wr_ptr, &pi); d.wr_ptr = pi; }
+    if (!rc) { rc = up(p, L.wc_ptr, &pi); d.wc_ptr = pi; }
+    { const uint8_t *p8 = nullptr; if (!rc) { rc = up(p, L.wc_cls, &p8); d.wc_cls = reinterpret_cast<const uint4 *>(p8); } }
+    if (!rc) { rc = up(p, L.row_mask, &pu); d.row_mask = pu; }
+    if (!rc) { rc = up(p, L.col_sig, &pu); d.col_sig = pu; }
+    if (!rc) { std::vector<int> z(1, 0); const int *pc = nullptr; rc = up(p, z, &pc); p->d_counter = const_cast<int *>(pc); }
+    if (rc) { edge_plan_destroy(p); return rc; }
+    p->L = std::move(L);
+    *out = p;
+    return QB_OK;
+}
+
+template <int THREADS, int MINB>
+static int launch_edge_t(EdgePlan *p, const MinsumLaunch &a, int grid, cudaStream_t st)
+{
+    QB_CUDA(cudaFuncSetAttribute(minsum_edge_kernel<THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    minsum_edge_kernel<THREADS, MINB><<<grid, THREADS, p->smem, st>>>(p->dev, a, p->d_counter);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+int launch_minsum_edge(qb_decoder *dec, EdgePlan *p, const MinsumLaunch &a, cudaStream_t st)
+{
+    QB_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
+    const int grid = std::max(1, std::min(a.B, dec->sm_count * p->ctas_per_sm));
+    if (p->threads == 1024) return launch_edge_t<1024, 1>(p, a, grid, st);
+    if (p->threads == 512) return launch_edge_t<512, 2>(p, a, grid, st);
+    return launch_edge_t<256, 4>(p, a, grid, st);
+}
+
+}  // namespace qb
