@@ -56,7 +56,7 @@ __device__ __forceinline__ float min_xorsign_abs(float a, float b)
 // ---- phase A: one row slice, K chunks of 4 edges per lane held in registers -------------------------------
 template <int K, bool FIRST>
 __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_unit, int stride, int lane,
-                                         uint32_t synsign, float alpha, uint2 pads)
+                                         uint32_t synsign, float alpha, float clip, uint2 pads)
 {
     float4 q[K];
     float4 *e4 = reinterpret_cast<float4 *>(E) + base_unit + lane;
@@ -78,10 +78,16 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
             m1s = min_xorsign_abs(m1s, v[i]);
         }
     }
+    // E holds the unclipped v - R; clip (kernels.py:330-333) is monotone in |Q| and keeps the sign, so the two
+    // smallest |clip(Q)| are min(., clip) of the two smallest |Q|: one clamp per row instead of one per edge
+    // (iteration 0 uses the priors unclipped, kernels.py:263-265: clip = +inf there)
     const float m1 = fabsf(m1s);
     const uint32_t tot = (__float_as_uint(m1s) & 0x80000000u) ^ synsign;      // kernels.py:289-298
-    uint32_t a1 = __float_as_uint(alpha * m1) ^ tot;                           // kernels.py:309-314
-    uint32_t a2 = __float_as_uint(alpha * m2) ^ tot;
+    // a row of degree 1 (three unused slots in a one-chunk row) has no second edge: its min2 stays +inf
+    float clip2 = clip;
+    if constexpr (K == 1) clip2 = ((pads.y & 0xFFFFu) != 0xFFFFu) ? INFINITY : clip;
+    uint32_t a1 = __float_as_uint(alpha * fminf(m1, clip)) ^ tot;              // kernels.py:309-314
+    uint32_t a2 = __float_as_uint(alpha * fminf(m2, clip2)) ^ tot;
     asm volatile("" : "+r"(a1), "+r"(a2));                  // keep the multiplications out of the per-edge code
 #pragma unroll
     for (int c = 0; c < K; ++c) {
@@ -104,7 +110,7 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
 // generic row (K > 9): two passes over shared memory
 template <bool FIRST>
 __device__ __noinline__ void row_task_loop(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
-                                           uint32_t synsign, float alpha, uint2 pads)
+                                           uint32_t synsign, float alpha, float clip, uint2 pads)
 {
     float4 *e4 = reinterpret_cast<float4 *>(E) + base_unit + lane;
     const float4 *g4 = E0 + base_unit + lane;
@@ -120,7 +126,7 @@ __device__ __noinline__ void row_task_loop(float *E, const float4 *E0, int base_
     }
     const float m1 = fabsf(m1s);
     const uint32_t tot = (__float_as_uint(m1s) & 0x80000000u) ^ synsign;
-    uint32_t a1 = __float_as_uint(alpha * m1) ^ tot, a2 = __float_as_uint(alpha * m2) ^ tot;
+    uint32_t a1 = __float_as_uint(alpha * fminf(m1, clip)) ^ tot, a2 = __float_as_uint(alpha * fminf(m2, clip)) ^ tot;
     asm volatile("" : "+r"(a1), "+r"(a2));
     for (int c = 0; c < K; ++c) {
         const float4 qq = FIRST ? __ldg(g4 + c * stride) : e4[c * stride];
@@ -141,49 +147,52 @@ __device__ __noinline__ void row_task_loop(float *E, const float4 *E0, int base_
 
 template <bool FIRST>
 __device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
-                                             uint32_t synsign, float alpha, uint2 pads)
+                                             uint32_t synsign, float alpha, float clip, uint2 pads)
 {
     switch (K) {
-    case 1: row_task<1, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 2: row_task<2, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 3: row_task<3, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 4: row_task<4, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 5: row_task<5, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 6: row_task<6, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 7: row_task<7, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 8: row_task<8, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    case 9: row_task<9, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, pads); break;
-    default: row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, pads); break;
+    case 1: row_task<1, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 2: row_task<2, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 3: row_task<3, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 4: row_task<4, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 5: row_task<5, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 6: row_task<6, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 7: row_task<7, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 8: row_task<8, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 9: row_task<9, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    default: row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, clip, pads); break;
     }
 }
 
 // ---- phase B ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v)); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v)); }
+// descriptors and slot indices are written once before the first barrier: plain (movable) loads
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
 
-// state shared by the column tasks of one warp during one phase B
+// state shared by the column tasks of one warp during one phase B (running pointers, one increment per task)
 struct ColCtx {
-    const uint2 *desc;      // shared: task descriptors {idx word offset of lane 0, prior}
-    const uint32_t *idx;    // shared: slot indices (absolute shared word addresses, see the staging loop), + lane
-    int t;                  // next task
-    float clip;
-    const uint32_t *sig;    // fingerprint table + lane
+    uint32_t desc;          // shared address of the next task descriptor {shared address of its index words, prior}
+    uint32_t lane4;
+    const uint32_t *sig;    // fingerprint of the next task's lane variable
     uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
-    uint32_t *hperm;        // hard-decision words
-    const uint16_t *vid;    // variable ids + lane (posterior output)
+    uint32_t hperm;         // shared address of the next hard-decision word
+    const uint16_t *vid;    // next task's variable id of the lane (posterior output)
     float *post;            // posterior row of the shot
     bool lane0;
 };
 
-// one full slice (32 variables) of degree D with a uniform prior
+// one full slice (32 variables) of degree D with a uniform prior.  E holds R on entry and the unclipped
+// v - R on exit (the clamp is applied per row in phase A).
 template <int D, bool EXACT, bool WRITE_V>
 __device__ __forceinline__ void col_task(ColCtx &c)
 {
-    const uint2 d = c.desc[c.t];
-    const uint32_t *ix = c.idx + d.x;
+    const uint2 d = lds_u64(c.desc);
+    const uint32_t ix = d.x + c.lane4;
     uint32_t w[(D + 1) / 2 + 1];
 #pragma unroll
-    for (int kk = 0; kk < (D + 1) / 2; ++kk) w[kk] = ix[kk * 32];
+    for (int kk = 0; kk < (D + 1) / 2; ++kk) w[kk] = lds_u32(ix + kk * 128);
     uint32_t addr[D + 1];
     float r[D + 1];
 #pragma unroll
@@ -199,19 +208,19 @@ __device__ __forceinline__ void col_task(ColCtx &c)
     for (int k = 0; k < D; ++k) {
         float q = v - r[k];                                // kernels.py:326
         if constexpr (EXACT) q = (q != q) ? 0.f : q;       // kernels.py:328-329
-        sts_f32(addr[k], fminf(fmaxf(q, -c.clip), c.clip));   // kernels.py:330-333
+        sts_f32(addr[k], q);
     }
     const bool neg = v < 0.f;                              // kernels.py:349
-    if (neg) c.fp ^= __ldg(c.sig + c.t * 32);
+    if (neg) c.fp ^= __ldg(c.sig);
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-    if (c.lane0) c.hperm[c.t] = hw;
-    if constexpr (WRITE_V) c.post[c.vid[c.t * 32]] = v;
-    c.t += 1;
+    if (c.lane0) sts_u32(c.hperm, hw);
+    if constexpr (WRITE_V) { c.post[*c.vid] = v; c.vid += 32; }
+    c.desc += 8; c.sig += 32; c.hperm += 4;
 }
 
 // any slice: partial, per-lane priors, large degree.  Returns the fingerprint contribution of the lane.
 template <bool WRITE_V>
-__device__ __noinline__ uint32_t col_task_generic(float *E, const uint32_t *idx /* global copy: E-relative slots */, uint2 gd, const float *lane_prior, int lane, float clip,
+__device__ __noinline__ uint32_t col_task_generic(float *E, const uint32_t *idx /* global copy: E-relative slots */, uint2 gd, const float *lane_prior, int lane,
                                                   const uint32_t *sig, uint32_t *hperm, const uint16_t *vid, float *post)
 {
     const int D = (gd.x >> 16) & 63, nl = (gd.x >> 22) & 63;
@@ -229,8 +238,7 @@ __device__ __noinline__ uint32_t col_task_generic(float *E, const uint32_t *idx 
             const uint32_t w = ix[(k >> 1) * 32];
             const uint32_t s = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
             float q = v - E[s];
-            q = (q != q) ? 0.f : q;
-            E[s] = fminf(fmaxf(q, -clip), clip);
+            E[s] = (q != q) ? 0.f : q;
         }
         neg = v < 0.f;
         if (neg) fp = __ldg(sig);
@@ -249,7 +257,8 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt)
 
 template <bool WRITE_V>
 __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, float *E, const uint32_t *gidx, const uint2 *gtask,
-                                        const float *lane_prior, int t0, int lane)
+                                        const float *lane_prior, int t0, int lane, const uint32_t *sig0, uint32_t *hperm0,
+                                        const uint16_t *vid0)
 {
     col_class<0, false, WRITE_V>(c, cls.x & 255);
     col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255);
@@ -272,8 +281,8 @@ __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, float *E, const ui
                            ((cls.y >> 16) & 255) + (cls.y >> 24) + (cls.z & 255) + ((cls.z >> 8) & 255) + ((cls.z >> 16) & 255) + (cls.z >> 24) +
                            (cls.w & 255) + ((cls.w >> 8) & 255) + ((cls.w >> 16) & 255));
         for (int i = 0; i < ngen; ++i, ++t) {
-            c.fp ^= col_task_generic<WRITE_V>(E, gidx, __ldg(&gtask[t]), lane_prior ? lane_prior + t * 32 : nullptr, lane, c.clip,
-                                              c.sig + t * 32, c.hperm + t, c.vid + t * 32, c.post);
+            c.fp ^= col_task_generic<WRITE_V>(E, gidx, __ldg(&gtask[t]), lane_prior ? lane_prior + t * 32 : nullptr, lane,
+                                              sig0 + t * 32, hperm0 + t, vid0 + t * 32, c.post);
         }
     }
 }
@@ -323,14 +332,16 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
     __shared__ int s_wt, s_next;
     __shared__ uint32_t s_fp[2], s_target;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __reduce_min_sync(0xFFFFFFFFu, tid >> 5);                       // provably warp-uniform
+    const uint32_t idx_addr = (uint32_t)__cvta_generic_to_shared(idx);
     // slot indices become absolute shared word addresses (E base folded in), so that a gather address is one
     // shift + one mask away from the packed pair
     const uint32_t e_word = (uint32_t)__cvta_generic_to_shared(E) >> 2;
     for (int i = tid; i < eg.idx_words; i += THREADS) idx[i] = eg.col_idx[i] + (e_word | (e_word << 16));
     for (int i = tid; i < eg.n_csl; i += THREADS) {
         const uint2 d = eg.ctask[i];
-        ctask[i] = make_uint2((d.x & 0xFFFFu) * 32u, d.y);
+        ctask[i] = make_uint2(idx_addr + (d.x & 0xFFFFu) * 128u, d.y);
     }
     for (int i = tid; i < eg.n_rsl; i += THREADS) rtask[i] = eg.rtask[i];
     const int r0 = eg.wr_ptr[warp], r1 = eg.wr_ptr[warp + 1];
@@ -370,25 +381,25 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
                 if (K == 0 || lane >= nl) continue;
                 const uint32_t synsign = ((syn[t] >> lane) & 1u) << 31;
                 const uint2 pads = __ldg(&eg.row_pads[t * 32 + lane]);
-                if (it == 0) row_dispatch<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, pads);
-                else row_dispatch<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, pads);
+                if (it == 0) row_dispatch<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, INFINITY, pads);
+                else row_dispatch<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, a.clip, pads);
             }
             if (tid == 0) s_fp[it & 1] = 0u;                                           // fingerprint accumulator of this iteration
             __syncthreads();
             // ---- phase B --------------------------------------------------------------------------------
             ColCtx c;
-            c.desc = ctask;
-            c.idx = idx + lane;
-            c.t = c0;
-            c.clip = a.clip;
-            c.sig = eg.col_sig + lane;
+            c.desc = (uint32_t)__cvta_generic_to_shared(ctask + c0);
+            c.lane4 = lane * 4;
+            c.sig = eg.col_sig + c0 * 32 + lane;
             c.fp = 0u;
-            c.hperm = hperm;
-            c.vid = eg.var_id + lane;
+            c.hperm = (uint32_t)__cvta_generic_to_shared(hperm + c0);
+            c.vid = eg.var_id + c0 * 32 + lane;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
             c.lane0 = lane == 0;
-            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane);
-            else phase_b<false>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane);
+            if (a.post && (api || it == a.max_iter - 1))
+                phase_b<true>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane, eg.col_sig + lane, hperm, eg.var_id + lane);
+            else
+                phase_b<false>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane, eg.col_sig + lane, hperm, eg.var_id + lane);
             const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp);
             if (lane == 0 && fp) atomicXor(&s_fp[it & 1], fp);
             __syncthreads();
@@ -550,6 +561,7 @@ int launch_minsum_edge(qb_decoder *dec, EdgePlan *p, const MinsumLaunch &a, cuda
     QB_CUDA(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
     const int grid = std::max(1, std::min(a.B, dec->sm_count * p->ctas_per_sm));
     if (p->threads == 1024) return launch_edge_t<1024, 1>(p, a, grid, st);
+    if (p->threads == 512 && p->ctas_per_sm == 1) return launch_edge_t<512, 1>(p, a, grid, st);
     if (p->threads == 512) return launch_edge_t<512, 2>(p, a, grid, st);
     return launch_edge_t<256, 4>(p, a, grid, st);
 }
