@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqldpc_b200.so")
+LIB_PATH = os.environ.get("QLDPC_B200_LIB", os.path.join(_HERE, "libqldpc_b200.so"))   # override: instrumented builds
 
 QB_ALPHA_FIXED, QB_ALPHA_DYNAMIC, QB_ALPHA_SEQUENCE = 0, 1, 2
 

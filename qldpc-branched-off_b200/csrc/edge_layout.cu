@@ -120,7 +120,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
         }
         for (auto &c : csl) {
             c.cls = 15;
-            if (c.vars.size() == 32 && L.uniform_prior) {
+            if ((c.vars.size() == 32 || c.prior >= 0.f) && L.uniform_prior) {
                 if (!c.exact && c.deg <= 8) c.cls = c.deg;
                 else if (c.exact && c.deg >= 1 && c.deg <= 6) c.cls = 8 + c.deg;
             }
@@ -138,7 +138,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     }
     {
         std::vector<int> cost(csl.size());
-        for (size_t i = 0; i < csl.size(); ++i) cost[i] = csl[i].deg * 2 + 5;
+        for (size_t i = 0; i < csl.size(); ++i) cost[i] = (csl[i].deg * 2 + 5) * (csl[i].cls == 15 ? 2 : 1);
         auto sched = lpt(cost, nwarps);
         std::vector<CSlice> re;
         L.wc_ptr.assign(nwarps + 1, 0);
@@ -151,6 +151,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                 L.wc_cls[(size_t)w * 16 + csl[t].cls]++;
             }
             L.wc_ptr[w + 1] = (int)re.size();
+            if (L.wc_ptr[w + 1] - L.wc_ptr[w] > 32) return fail("more than 32 column slices per warp");
         }
         csl.swap(re);
     }
@@ -167,7 +168,8 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
         words += rsl[t].K * rs_stride[t] * 4;
         for (int l = 0; l < nl; ++l) { row_slice[rsl[t].rows[l]] = t; row_lane[rsl[t].rows[l]] = l; }
     }
-    L.e_words = std::max(4, words);
+    L.e_dummy = std::max(4, words);
+    L.e_words = L.e_dummy + 32;
     if (L.e_words >= 65000) return fail("edge array above 65000 words");
     auto slot_word = [&](int t, int lane, int slot) { return rs_base[t] + ((slot >> 2) * rs_stride[t] + lane) * 4 + (slot & 3); };
 
@@ -264,6 +266,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     L.row_id.assign((size_t)L.n_rsl * 32, 0xFFFFu);
     L.row_pads.assign((size_t)L.n_rsl * 32 * 4, 0xFFFFu);
     L.slot_var.assign(L.e_words, -1);
+    for (int i = L.e_dummy; i < L.e_words; ++i) L.slot_var[i] = -2;
     for (int t = 0; t < L.n_rsl; ++t) {
         const int nl = (int)rsl[t].rows.size();
         L.rtask[2 * t] = (uint32_t)rs_base[t];
@@ -313,11 +316,20 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                 const uint32_t slot = (uint32_t)slot_word(row_slice[r], row_lane[r], slot_of[e]);
                 const uint32_t rpos = (uint32_t)(row_slice[r] * 32 + row_lane[r]);
                 L.col_sig[t * 32 + l] ^= L.row_mask[rpos];
-                uint32_t &wi = L.col_idx[cs_base[t] + (k >> 1) * 32 + l];
-                uint32_t &wr = L.col_rowpos[cs_base[t] + (k >> 1) * 32 + l];
+                const int H = (csl[t].deg + 1) / 2;
+                uint32_t &wi = L.col_idx[cs_base[t] + edge_idx_off(H, k >> 1, l)];
+                uint32_t &wr = L.col_rowpos[cs_base[t] + edge_idx_off(H, k >> 1, l)];
                 if (k & 1) { wi = (wi & 0x0000FFFFu) | (slot << 16); wr = (wr & 0x0000FFFFu) | (rpos << 16); }
                 else { wi = (wi & 0xFFFF0000u) | slot; wr = (wr & 0xFFFF0000u) | rpos; }
             }
+        }
+        if (csl[t].cls != 15) {          // dummy lanes of a partial slice on the fast path
+            const int H = (csl[t].deg + 1) / 2;
+            for (int l = nl; l < 32; ++l)
+                for (int kk = 0; kk < H; ++kk) {
+                    const uint32_t slot = (uint32_t)(L.e_dummy + l);
+                    L.col_idx[cs_base[t] + edge_idx_off(H, kk, l)] = slot | (slot << 16);
+                }
         }
     }
     L.ok = true;
@@ -349,7 +361,7 @@ extern "C" int qb_edge_layout_probe(int32_t m, int32_t n, const int32_t *indptr,
         const int base = (int)(L.ctask[2 * t] & 0xFFFFu) * 32, deg = (int)((L.ctask[2 * t] >> 16) & 63u), nl = (int)((L.ctask[2 * t] >> 22) & 63u);
         for (int l = 0; l < nl; ++l)
             for (int k = 0; k < deg; ++k) {
-                const uint32_t w = L.col_idx[base + (k >> 1) * 32 + l];
+                const uint32_t w = L.col_idx[base + qb::edge_idx_off((deg + 1) / 2, k >> 1, l)];
                 const int slot = (k & 1) ? (int)(w >> 16) : (int)(w & 0xFFFFu);
                 if (slot >= L.e_words || L.slot_var[slot] != (int)L.var_id[t * 32 + l] || seen[slot]++) good = false;
                 ++cnt;

@@ -12,7 +12,9 @@
 //   so the 8 lanes of a quarter warp cover the 32 banks and the bank of a slot is ((c + lane) * 4 + i) mod 32
 //   up to the base: every row sees every bank.  Unused slots (>= 1, <= 4 per row) hold +inf.
 // Column slices hold <= 32 variables of equal degree (and equal prior when priors take few distinct values);
-// their slot indices are stored as uint16 pairs, SoA: idx[base + kk * 32 + lane] = slot(2kk) | slot(2kk+1) << 16.
+// their slot indices are stored as uint16 pairs: idx[base + edge_idx_off(H, kk, lane)] = slot(2kk) | slot(2kk+1) << 16.
+// A slice with fewer than 32 variables and a non-negative prior is filled with dummy lanes whose indices all point
+// at a private dummy word behind the row slices (value 0 at start, never negative), so that it takes the fast path.
 // Slices are numbered in per-warp task order (LPT schedule), warp w owns [wr_ptr[w], wr_ptr[w+1]) and
 // [wc_ptr[w], wc_ptr[w+1]).
 #pragma once
@@ -21,7 +23,21 @@
 #include <string>
 #include <vector>
 
+#if defined(__CUDACC__)
+#define QB_HD __host__ __device__
+#else
+#define QB_HD
+#endif
+
 namespace qb {
+
+// Word offset, inside the index block of a column slice with H = ceil(degree / 2) index words per variable, of
+// word kk of the variable in `lane`: the words are stored two per lane (one LDS.64 fetches 4 slot indices), an odd
+// last word one per lane.
+QB_HD inline int edge_idx_off(int H, int kk, int lane)
+{
+    return (kk >> 1) * 64 + ((kk == H - 1 && (H & 1)) ? lane : lane * 2 + (kk & 1));
+}
 
 struct EdgeLayout {
     bool ok = false;
@@ -29,7 +45,8 @@ struct EdgeLayout {
     int m = 0, n = 0, nnz = 0;
     int nwarps = 0;
     int n_rsl = 0, n_csl = 0;
-    int e_words = 0;                     // size of E in words (multiple of 4)
+    int e_words = 0;                     // size of E in words (multiple of 4), including 32 dummy words at the end
+    int e_dummy = 0;                     // first dummy word
     int idx_words = 0;                   // size of the column index table in words (multiple of 32)
     int max_K = 0, max_cdeg = 0;
     bool uniform_prior = false;          // every column slice has one prior value (else per-lane priors, lane_prior)
@@ -43,7 +60,7 @@ struct EdgeLayout {
     std::vector<uint32_t> col_idx;       // [idx_words] slot pairs
     std::vector<uint32_t> col_rowpos;    // [idx_words] permuted row position (slice*32+lane) pairs, same layout
     std::vector<float> lane_prior;       // [n_csl*32] (only when !uniform_prior)
-    std::vector<int32_t> slot_var;       // [e_words] variable of each slot, -1 = unused
+    std::vector<int32_t> slot_var;       // [e_words] variable of each slot, -1 = unused (+inf), -2 = dummy (0)
     std::vector<int32_t> wr_ptr, wc_ptr; // [nwarps+1]
     // column slices of a warp are sorted by class: 0..8 = full slice of degree 0..8, uniform prior;
     // 9..14 = same for variables next to a degree-1 row (NaN handling), degree 1..6; 15 = everything else

@@ -30,7 +30,7 @@
 namespace qb {
 
 struct EdgeDev {
-    int n_rsl, n_csl, e_words, idx_words, nw, n, mw;
+    int n_rsl, n_csl, e_words, e_dummy, idx_words, nw, n, mw;
     const float4 *E0;            // [e_words/4] prior per slot, +inf in unused slots
     const uint32_t *col_idx;     // [idx_words]
     const uint32_t *col_rowpos;  // [idx_words]
@@ -95,8 +95,15 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
         float r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            // sign(Q) is moved into bit 31 with two multiply-adds (fma pipe; the alu pipe is the busy one here):
+            // adding 2^31 to a word whose low 31 bits are untouched flips its sign bit
             const uint32_t sel = (fabsf(v[i]) == m1) ? a2 : a1;
+#ifndef QB_EDGE_IMAD_SIGN
             r[i] = __uint_as_float(sel ^ (__float_as_uint(v[i]) & 0x80000000u));
+#else
+            const uint32_t sb = __umulhi(__float_as_uint(v[i]), 2u);
+            r[i] = __uint_as_float(sb * 0x80000000u + sel);
+#endif
         }
         e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
     }
@@ -169,122 +176,182 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v)); }
 // descriptors and slot indices are written once before the first barrier: plain (movable) loads
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ uint2 lds_u64(uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
 
-// state shared by the column tasks of one warp during one phase B (running pointers, one increment per task)
+// per-slice priors travel in the kernel parameters (constant bank): a warp-uniform index makes them uniform
+// loads, off the shared-memory pipe that bounds phase B
+constexpr int EDGE_MAX_CSL = 768;
+struct EdgePriors { uint32_t bits[EDGE_MAX_CSL]; };
+
+// state shared by the column tasks of one warp during one phase B (the index blocks, fingerprints and priors of
+// consecutive tasks are consecutive in memory)
 struct ColCtx {
-    uint32_t desc;          // shared address of the next task descriptor {shared address of its index words, prior}
-    uint32_t lane4;
-    const uint32_t *sig;    // fingerprint of the next task's lane variable
+    uint32_t ix;            // shared address of the index block of the next task
+    uint32_t lane4, lane8;
+    uint32_t sg;            // shared address of the 8-bit fingerprint of the next task's lane variable
     uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
-    uint32_t hperm;         // shared address of the next hard-decision word
+    uint32_t myhw;          // lane j keeps the hard-decision word of the warp's j-th task
+    int t, t0;              // next task, first task of the warp
+    int lane;
     const uint16_t *vid;    // next task's variable id of the lane (posterior output)
     float *post;            // posterior row of the shot
-    bool lane0;
 };
 
-// one full slice (32 variables) of degree D with a uniform prior.  E holds R on entry and the unclipped
-// v - R on exit (the clamp is applied per row in phase A).
-template <int D, bool EXACT, bool WRITE_V>
-__device__ __forceinline__ void col_task(ColCtx &c)
+// index words of task (t + j) of a run of degree-D slices starting at c.ix: two words per LDS.64
+template <int D>
+__device__ __forceinline__ void load_idx_words(const ColCtx &c, int j, uint32_t (&w)[(D + 1) / 2 + 1])
 {
-    const uint2 d = lds_u64(c.desc);
-    const uint32_t ix = d.x + c.lane4;
-    uint32_t w[(D + 1) / 2 + 1];
+    constexpr int H = (D + 1) / 2;
+    const uint32_t base = c.ix + j * H * 128;
 #pragma unroll
-    for (int kk = 0; kk < (D + 1) / 2; ++kk) w[kk] = lds_u32(ix + kk * 128);
-    uint32_t addr[D + 1];
-    float r[D + 1];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        addr[k] = (k & 1) ? ((w[k >> 1] >> 14) & 0x3FFFCu) : ((w[k >> 1] << 2) & 0x3FFFCu);
-        r[k] = lds_f32(addr[k]);
+    for (int u = 0; u < H / 2; ++u) {
+        const uint2 p = lds_u64(base + u * 256 + c.lane8);
+        w[2 * u] = p.x; w[2 * u + 1] = p.y;
     }
-    float acc = D > 0 ? r[0] : 0.f;                        // kernels.py:316 (row order)
-#pragma unroll
-    for (int k = 1; k < D; ++k) acc += r[k];
-    const float v = acc + __uint_as_float(d.y);            // kernels.py:320
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        float q = v - r[k];                                // kernels.py:326
-        if constexpr (EXACT) q = (q != q) ? 0.f : q;       // kernels.py:328-329
-        sts_f32(addr[k], q);
-    }
-    const bool neg = v < 0.f;                              // kernels.py:349
-    if (neg) c.fp ^= __ldg(c.sig);
-    const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-    if (c.lane0) sts_u32(c.hperm, hw);
-    if constexpr (WRITE_V) { c.post[*c.vid] = v; c.vid += 32; }
-    c.desc += 8; c.sig += 32; c.hperm += 4;
+    if constexpr (H & 1) w[H - 1] = lds_u32(base + (H / 2) * 256 + c.lane4);
 }
 
-// any slice: partial, per-lane priors, large degree.  Returns the fingerprint contribution of the lane.
-template <bool WRITE_V>
-__device__ __noinline__ uint32_t col_task_generic(float *E, const uint32_t *idx /* global copy: E-relative slots */, uint2 gd, const float *lane_prior, int lane,
-                                                  const uint32_t *sig, uint32_t *hperm, const uint16_t *vid, float *post)
+// Groups of N consecutive slices of one class, software pipelined (see col_class).
+template <int D, int N>
+struct ColGroup {
+    uint32_t addr[N][D + 1];
+    float r[N][D + 1];
+};
+
+template <int D, int N>
+__device__ __forceinline__ void group_load_idx(const ColCtx &c, int g, uint32_t (&w)[N][(D + 1) / 2 + 1])
 {
-    const int D = (gd.x >> 16) & 63, nl = (gd.x >> 22) & 63;
-    const uint32_t *ix = idx + (gd.x & 0xFFFFu) * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < N; ++j) load_idx_words<D>(c, g * N + j, w[j]);
+}
+
+template <int D, int N>
+__device__ __forceinline__ void group_gather(const uint32_t (&w)[N][(D + 1) / 2 + 1], ColGroup<D, N> &G)
+{
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            G.addr[j][k] = (k & 1) ? ((w[j][k >> 1] >> 14) & 0x3FFFCu) : ((w[j][k >> 1] << 2) & 0x3FFFCu);
+            G.r[j][k] = lds_f32(G.addr[j][k]);
+        }
+}
+
+// E holds R on entry and the unclipped v - R on exit (the clamp is applied per row in phase A)
+template <int D, bool EXACT, bool WRITE_V, int N>
+__device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G, const EdgePriors &pri)
+{
+    float v[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        float acc = D > 0 ? G.r[j][0] : 0.f;               // kernels.py:316 (row order)
+#pragma unroll
+        for (int k = 1; k < D; ++k) acc += G.r[j][k];
+        v[j] = acc + __uint_as_float(pri.bits[c.t + j]);   // kernels.py:320
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float q = v[j] - G.r[j][k];                    // kernels.py:326
+            if constexpr (EXACT) q = (q != q) ? 0.f : q;   // kernels.py:328-329
+            sts_f32(G.addr[j][k], q);
+        }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const bool neg = v[j] < 0.f;                       // kernels.py:349
+        if (neg) c.fp ^= lds_u8(c.sg + 32 * j);
+        const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
+        if (c.lane == c.t + j - c.t0) c.myhw = hw;
+        if constexpr (WRITE_V) { const uint32_t vid = c.vid[32 * j]; if (vid != 0xFFFFu) c.post[vid] = v[j]; }
+    }
+    if constexpr (WRITE_V) c.vid += 32 * N;
+    c.ix += N * ((D + 1) / 2) * 128; c.sg += 32 * N; c.t += N;
+}
+
+// any slice: partial with a negative prior, per-lane priors, large degree (meta = degree << 16 | lanes << 22)
+template <bool WRITE_V>
+__device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const float *lane_prior, const EdgePriors &pri)
+{
+    const int D = (meta >> 16) & 63, nl = (meta >> 22) & 63, H = (D + 1) >> 1;
     bool neg = false;
-    uint32_t fp = 0u;
-    if (lane < nl) {
+    if (c.lane < nl) {
         float acc = 0.f;
         for (int k = 0; k < D; ++k) {
-            const uint32_t w = ix[(k >> 1) * 32];
-            acc += E[(k & 1) ? (w >> 16) : (w & 0xFFFFu)];
+            const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
+            acc += lds_f32((k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu));
         }
-        const float v = acc + (lane_prior ? lane_prior[lane] : __uint_as_float(gd.y));
+        const float v = acc + (lane_prior ? __ldg(lane_prior) : __uint_as_float(pri.bits[c.t]));
         for (int k = 0; k < D; ++k) {
-            const uint32_t w = ix[(k >> 1) * 32];
-            const uint32_t s = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
-            float q = v - E[s];
-            E[s] = (q != q) ? 0.f : q;
+            const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
+            const uint32_t addr = (k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu);
+            const float q = v - lds_f32(addr);
+            sts_f32(addr, (q != q) ? 0.f : q);
         }
         neg = v < 0.f;
-        if (neg) fp = __ldg(sig);
-        if (WRITE_V) post[*vid] = v;
+        if (neg) c.fp ^= lds_u8(c.sg);
+        if (WRITE_V) c.post[*c.vid] = v;
     }
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-    if (lane == 0) *hperm = hw;
-    return fp;
+    if (c.lane == c.t - c.t0) c.myhw = hw;
+    if (WRITE_V) c.vid += 32;
+    c.ix += H * 128; c.sg += 32; c.t += 1;
 }
 
+// Software-pipelined groups of N consecutive slices of one class: the index words of group g+2 and the gathers
+// of group g+1 are in flight while group g is summed and scattered (the slots of different slices are disjoint).
 template <int D, bool EXACT, bool WRITE_V>
-__device__ __forceinline__ void col_class(ColCtx &c, int cnt)
+__device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &pri)
 {
-    for (int i = 0; i < cnt; ++i) col_task<D, EXACT, WRITE_V>(c);
+    constexpr int N = (D <= 4) ? 2 : 1;
+    int ng = cnt / N;
+    if (ng > 0) {
+        uint32_t w[N][(D + 1) / 2 + 1];
+        ColGroup<D, N> G, G2;
+        group_load_idx<D, N>(c, 0, w);
+        group_gather<D, N>(w, G);
+        group_load_idx<D, N>(c, 1, w);                     // may read past the class (never past the table region): unused then
+        for (; ng > 1; --ng) {
+            group_gather<D, N>(w, G2);
+            group_load_idx<D, N>(c, 2, w);
+            group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
+            G = G2;
+        }
+        group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
+    }
+    if constexpr (N == 2) {
+        if (cnt & 1) {
+            uint32_t w[1][(D + 1) / 2 + 1];
+            ColGroup<D, 1> G;
+            group_load_idx<D, 1>(c, 0, w);
+            group_gather<D, 1>(w, G);
+            group_finish<D, EXACT, WRITE_V, 1>(c, G, pri);
+        }
+    }
 }
 
 template <bool WRITE_V>
-__device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, float *E, const uint32_t *gidx, const uint2 *gtask,
-                                        const float *lane_prior, int t0, int lane, const uint32_t *sig0, uint32_t *hperm0,
-                                        const uint16_t *vid0)
+__device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, const uint32_t *cmeta, const float *lane_prior, const EdgePriors &pri)
 {
-    col_class<0, false, WRITE_V>(c, cls.x & 255);
-    col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255);
-    col_class<2, false, WRITE_V>(c, (cls.x >> 16) & 255);
-    col_class<3, false, WRITE_V>(c, cls.x >> 24);
-    col_class<4, false, WRITE_V>(c, cls.y & 255);
-    col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255);
-    col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255);
-    col_class<7, false, WRITE_V>(c, cls.y >> 24);
-    col_class<8, false, WRITE_V>(c, cls.z & 255);
-    col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255);
-    col_class<2, true, WRITE_V>(c, (cls.z >> 16) & 255);
-    col_class<3, true, WRITE_V>(c, cls.z >> 24);
-    col_class<4, true, WRITE_V>(c, cls.w & 255);
-    col_class<5, true, WRITE_V>(c, (cls.w >> 8) & 255);
-    col_class<6, true, WRITE_V>(c, (cls.w >> 16) & 255);
+    col_class<0, false, WRITE_V>(c, cls.x & 255, pri);
+    col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255, pri);
+    col_class<2, false, WRITE_V>(c, (cls.x >> 16) & 255, pri);
+    col_class<3, false, WRITE_V>(c, cls.x >> 24, pri);
+    col_class<4, false, WRITE_V>(c, cls.y & 255, pri);
+    col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255, pri);
+    col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255, pri);
+    col_class<7, false, WRITE_V>(c, cls.y >> 24, pri);
+    col_class<8, false, WRITE_V>(c, cls.z & 255, pri);
+    col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255, pri);
+    col_class<2, true, WRITE_V>(c, (cls.z >> 16) & 255, pri);
+    col_class<3, true, WRITE_V>(c, cls.z >> 24, pri);
+    col_class<4, true, WRITE_V>(c, cls.w & 255, pri);
+    col_class<5, true, WRITE_V>(c, (cls.w >> 8) & 255, pri);
+    col_class<6, true, WRITE_V>(c, (cls.w >> 16) & 255, pri);
     const int ngen = cls.w >> 24;
-    if (ngen) {
-        int t = t0 + (int)((cls.x & 255) + ((cls.x >> 8) & 255) + ((cls.x >> 16) & 255) + (cls.x >> 24) + (cls.y & 255) + ((cls.y >> 8) & 255) +
-                           ((cls.y >> 16) & 255) + (cls.y >> 24) + (cls.z & 255) + ((cls.z >> 8) & 255) + ((cls.z >> 16) & 255) + (cls.z >> 24) +
-                           (cls.w & 255) + ((cls.w >> 8) & 255) + ((cls.w >> 16) & 255));
-        for (int i = 0; i < ngen; ++i, ++t) {
-            c.fp ^= col_task_generic<WRITE_V>(E, gidx, __ldg(&gtask[t]), lane_prior ? lane_prior + t * 32 : nullptr, lane,
-                                              sig0 + t * 32, hperm0 + t, vid0 + t * 32, c.post);
-        }
-    }
+    for (int i = 0; i < ngen; ++i)
+        col_task_generic<WRITE_V>(c, cmeta[c.t], lane_prior ? lane_prior + c.t * 32 + c.lane : nullptr, pri);
 }
 
 // weight of the residual syndrome par ^ syn (0 = converged); resets par.  Called by warp 0 only.
@@ -302,13 +369,13 @@ __device__ __forceinline__ void parity_of_hard(const EdgeDev &eg, const uint32_t
         uint32_t bits = hperm[t];
         if (!bits) continue;
         const uint32_t dx = __ldg(&eg.ctask[t]).x;
-        const int D = (dx >> 16) & 63;
+        const int D = (dx >> 16) & 63, H = (D + 1) >> 1;
         const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
             for (int k = 0; k < D; ++k) {
-                const uint32_t w = __ldg(&rp[(k >> 1) * 32 + b]);
+                const uint32_t w = __ldg(&rp[edge_idx_off(H, k >> 1, b)]);
                 const uint32_t pos = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
                 atomicXor(&par[pos >> 5], 1u << (pos & 31));
             }
@@ -316,19 +383,34 @@ __device__ __forceinline__ void parity_of_hard(const EdgeDev &eg, const uint32_t
     }
 }
 
+#ifdef QB_EDGE_PROFILE
+__device__ unsigned long long g_edge_prof[256 * 32 * 4];   // [cta][warp]{phase A work, wait 1, phase B work, wait 2} cycles
+#define PROF_T(x) long long x; asm volatile("mov.u64 %0, %%clock64;" : "=l"(x) :: "memory")
+// BAR.SYNC does not block at issue: a read of barrier-protected shared memory and a branch on its value do
+#define PROF_BLOCK() do { unsigned d_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d_) : "r"((unsigned)__cvta_generic_to_shared(&s_wt)) : "memory"); \
+                          if (d_ == 0x7FFFFFF1u) prof[0] += 1; } while (0)
+#define PROF_ADD(i, d) prof[i] += (unsigned long long)(d)
+#else
+#define PROF_T(x)
+#define PROF_ADD(i, d)
+#define PROF_BLOCK()
+#endif
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
+minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ MinsumLaunch a, int *shot_counter,
+                   const __grid_constant__ EdgePriors pri)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *E = reinterpret_cast<float *>(smem_raw);                                   // [e_words]
     uint32_t *idx = reinterpret_cast<uint32_t *>(E + eg.e_words);                     // [idx_words]
-    uint2 *ctask = reinterpret_cast<uint2 *>(idx + eg.idx_words);                     // [n_csl] {idx address, prior}
-    uint2 *rtask = ctask + eg.n_csl;                                                  // [n_rsl]
+    uint2 *rtask = reinterpret_cast<uint2 *>(idx + eg.idx_words);                     // [n_rsl]
     uint32_t *syn = reinterpret_cast<uint32_t *>(rtask + eg.n_rsl);                   // [n_rsl] permuted syndrome bits
     uint32_t *par = syn + eg.n_rsl;                                                   // [n_rsl] parity of the hard decision
-    uint32_t *hperm = par + eg.n_rsl;                                                 // [n_csl] hard decision, slice order
+    uint32_t *hperm = par + eg.n_rsl;                                                 // [n_csl] hard decision word per column slice
     uint32_t *hnat = hperm + eg.n_csl;                                                // [nw] hard decision, natural order
+    uint32_t *cmeta = hnat + eg.nw;                                                   // [n_csl] degree / lanes of every column slice
+    uint8_t *csig = reinterpret_cast<uint8_t *>(cmeta + eg.n_csl);                    // [n_csl*32] 8-bit fingerprint per variable
     __shared__ int s_wt, s_next;
     __shared__ uint32_t s_fp[2], s_target;
 
@@ -341,16 +423,25 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
     for (int i = tid; i < eg.idx_words; i += THREADS) idx[i] = eg.col_idx[i] + (e_word | (e_word << 16));
     for (int i = tid; i < eg.n_csl; i += THREADS) {
         const uint2 d = eg.ctask[i];
-        ctask[i] = make_uint2(idx_addr + (d.x & 0xFFFFu) * 128u, d.y);
+        cmeta[i] = d.x;
+        hperm[i] = 0u;
     }
     for (int i = tid; i < eg.n_rsl; i += THREADS) rtask[i] = eg.rtask[i];
+    for (int i = tid; i < eg.n_csl * 32; i += THREADS) csig[i] = (uint8_t)eg.col_sig[i];
+    if (tid < 32) E[eg.e_dummy + tid] = 0.f;                                         // dummy lanes of partial column slices
     const int r0 = eg.wr_ptr[warp], r1 = eg.wr_ptr[warp + 1];
     const int c0 = eg.wc_ptr[warp];
     const uint4 cls = eg.wc_cls[warp];
+    const int c1 = eg.wc_ptr[warp + 1];
+    // shared address of the index block of the warp's first column slice
+    const uint32_t ix0 = idx_addr + (c0 < eg.n_csl ? (eg.ctask[c0].x & 0xFFFFu) * 128u : 0u);
     if (tid == 0) { s_next = atomicAdd(shot_counter, 1); s_fp[0] = 0u; s_fp[1] = 0u; s_target = 0u; }
     __syncthreads();
     int shot = s_next;
     const bool api = !a.post_failed_only;
+#ifdef QB_EDGE_PROFILE
+    unsigned long long prof[4] = {0, 0, 0, 0};
+#endif
 
     while (shot < a.B) {                                                              // uniform
         // ---- load: permuted syndrome words and their fingerprint, parity = 0 ----------------------------------
@@ -359,7 +450,7 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
             for (int t = warp; t < eg.n_rsl; t += THREADS / 32) {
                 const uint32_t rid = eg.row_id[t * 32 + lane];
                 const bool bit = rid != 0xFFFFu && ((a.syn_bits[(size_t)shot * eg.mw + (rid >> 5)] >> (rid & 31)) & 1u);
-                if (bit) tg ^= eg.row_mask[t * 32 + lane];
+                if (bit) tg ^= eg.row_mask[t * 32 + lane] & 0xFFu;
                 const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
                 if (lane == 0) { syn[t] = word; par[t] = 0u; }
             }
@@ -375,6 +466,8 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
         for (int it = 0; it < a.max_iter; ++it) {
             // ---- phase A --------------------------------------------------------------------------------
             const float alpha = a.alpha_d[it];
+            PROF_T(t0);
+#ifndef QB_EDGE_SKIP_A
             for (int t = r0; t < r1; ++t) {
                 const uint2 d = rtask[t];
                 const int K = d.y & 255, nl = (d.y >> 8) & 255, stride = d.y >> 16;
@@ -384,25 +477,33 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
                 if (it == 0) row_dispatch<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, INFINITY, pads);
                 else row_dispatch<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, a.clip, pads);
             }
+#endif
             if (tid == 0) s_fp[it & 1] = 0u;                                           // fingerprint accumulator of this iteration
+            PROF_T(t1);
             __syncthreads();
+            PROF_BLOCK();
+            PROF_T(t2);
             // ---- phase B --------------------------------------------------------------------------------
             ColCtx c;
-            c.desc = (uint32_t)__cvta_generic_to_shared(ctask + c0);
-            c.lane4 = lane * 4;
-            c.sig = eg.col_sig + c0 * 32 + lane;
-            c.fp = 0u;
-            c.hperm = (uint32_t)__cvta_generic_to_shared(hperm + c0);
+            c.ix = ix0;
+            c.lane4 = lane * 4; c.lane8 = lane * 8;
+            c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
+            c.fp = 0u; c.myhw = 0u;
+            c.t = c0; c.t0 = c0; c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
-            c.lane0 = lane == 0;
-            if (a.post && (api || it == a.max_iter - 1))
-                phase_b<true>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane, eg.col_sig + lane, hperm, eg.var_id + lane);
-            else
-                phase_b<false>(c, cls, E, eg.col_idx, eg.ctask, eg.lane_prior, c0, lane, eg.col_sig + lane, hperm, eg.var_id + lane);
+#ifndef QB_EDGE_SKIP_B
+            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, cmeta, eg.lane_prior, pri);
+            else phase_b<false>(c, cls, cmeta, eg.lane_prior, pri);
+#endif
+            if (lane < c1 - c0) hperm[c0 + lane] = c.myhw;
             const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp);
             if (lane == 0 && fp) atomicXor(&s_fp[it & 1], fp);
+            PROF_T(t3);
             __syncthreads();
+            PROF_BLOCK();
+            PROF_T(t4);
+            PROF_ADD(0, t1 - t0); PROF_ADD(1, t2 - t1); PROF_ADD(2, t3 - t2); PROF_ADD(3, t4 - t3);
             // ---- convergence: fingerprint of H.hard against the syndrome's, exact test only on a match -----
             if (s_fp[it & 1] == target) {                                              // uniform
                 parity_of_hard(eg, hperm, par, tid, THREADS);
@@ -446,6 +547,10 @@ minsum_edge_kernel(EdgeDev eg, MinsumLaunch a, int *shot_counter)
         shot = s_next;
         __syncthreads();
     }
+#ifdef QB_EDGE_PROFILE
+    if (lane == 0 && blockIdx.x < 256)
+        for (int i = 0; i < 4; ++i) g_edge_prof[(blockIdx.x * 32 + warp) * 4 + i] = prof[i];
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -458,12 +563,13 @@ struct EdgePlan {
     int *d_counter = nullptr;
     int threads = 0, ctas_per_sm = 0;
     size_t smem = 0;
+    EdgePriors pri{};
 };
 
 static size_t edge_smem_bytes(const EdgeLayout &L, int nw)
 {
     return (size_t)L.e_words * 4 + (size_t)L.idx_words * 4 + (size_t)L.n_csl * 8 + (size_t)L.n_rsl * 8 +
-           (size_t)L.n_rsl * 8 + (size_t)L.n_csl * 4 + (size_t)nw * 4 + 64;
+           (size_t)L.n_rsl * 8 + (size_t)L.n_csl * 4 + (size_t)nw * 4 + (size_t)L.n_csl * 32 + 64;
 }
 
 template <class T>
@@ -487,7 +593,10 @@ void edge_plan_destroy(EdgePlan *p)
 static std::vector<float> edge_E0(const EdgeLayout &L, const float *prior)
 {
     std::vector<float> e0(L.e_words, INFINITY);
-    for (int i = 0; i < L.e_words; ++i) if (L.slot_var[i] >= 0) e0[i] = prior[L.slot_var[i]] + 0.0f;   // -0.0 -> +0.0
+    for (int i = 0; i < L.e_words; ++i) {
+        if (L.slot_var[i] >= 0) e0[i] = prior[L.slot_var[i]] + 0.0f;   // -0.0 -> +0.0
+        else if (L.slot_var[i] == -2) e0[i] = 0.f;
+    }
     return e0;
 }
 
@@ -502,7 +611,7 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     const size_t limit = (size_t)dec->max_smem_optin;
     int nwarps = 32;
     EdgeLayout L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
-    if (!L.ok) return QB_OK;
+    if (!L.ok || L.n_csl > EDGE_MAX_CSL) return QB_OK;
     size_t smem = edge_smem_bytes(L, g.nw);
     if (smem > limit) return QB_OK;
     // several CTAs per SM for small codes: fewer warps each
@@ -520,7 +629,7 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     EdgePlan *p = new EdgePlan();
     p->threads = nwarps * 32; p->ctas_per_sm = ctas; p->smem = smem;
     EdgeDev &d = p->dev;
-    d.n_rsl = L.n_rsl; d.n_csl = L.n_csl; d.e_words = L.e_words; d.idx_words = L.idx_words;
+    d.n_rsl = L.n_rsl; d.n_csl = L.n_csl; d.e_words = L.e_words; d.e_dummy = L.e_dummy; d.idx_words = L.idx_words;
     d.nw = g.nw; d.n = g.n; d.mw = g.mw;
     int rc = QB_OK;
     const std::vector<float> e0 = edge_E0(L, prior_h);
@@ -542,6 +651,7 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     if (!rc) { rc = up(p, L.col_sig, &pu); d.col_sig = pu; }
     if (!rc) { std::vector<int> z(1, 0); const int *pc = nullptr; rc = up(p, z, &pc); p->d_counter = const_cast<int *>(pc); }
     if (rc) { edge_plan_destroy(p); return rc; }
+    for (int t = 0; t < L.n_csl; ++t) p->pri.bits[t] = L.ctask[2 * t + 1];
     p->L = std::move(L);
     *out = p;
     return QB_OK;
@@ -551,10 +661,17 @@ template <int THREADS, int MINB>
 static int launch_edge_t(EdgePlan *p, const MinsumLaunch &a, int grid, cudaStream_t st)
 {
     QB_CUDA(cudaFuncSetAttribute(minsum_edge_kernel<THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    minsum_edge_kernel<THREADS, MINB><<<grid, THREADS, p->smem, st>>>(p->dev, a, p->d_counter);
+    minsum_edge_kernel<THREADS, MINB><<<grid, THREADS, p->smem, st>>>(p->dev, a, p->d_counter, p->pri);
     QB_CUDA(cudaGetLastError());
     return QB_OK;
 }
+
+#ifdef QB_EDGE_PROFILE
+extern "C" int qb_debug_edge_profile(unsigned long long *out_h)
+{
+    return cudaMemcpyFromSymbol(out_h, g_edge_prof, sizeof(g_edge_prof)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int launch_minsum_edge(qb_decoder *dec, EdgePlan *p, const MinsumLaunch &a, cudaStream_t st)
 {
