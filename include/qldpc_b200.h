@@ -65,6 +65,17 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr_h,
                       const double *prior_h, int32_t k, const int32_t *logical_ptr_h,
                       const int32_t *logical_idx_h, qb_decoder **out);
 int qb_decoder_set_prior(qb_decoder *dec, const double *prior_h);
+
+/* Host-only (no CUDA call): statistics of the shared-memory layout the per-edge min-sum kernel would use for this
+ * graph (csrc/edge_layout.h): one float per Tanner-graph edge, check rows in conflict-free 128-bit order, the slot of
+ * every edge chosen so that the 32 gathers of one warp instruction of the variable phase hit 32 different banks.
+ * stats_out[16] = { usable, row slices, column slices, edge words, index words, gather instructions per iteration,
+ *   shared-memory wavefronts they need (equal when conflict free), edges still in a bank conflict, priors uniform per
+ *   slice, max chunks per row, max column degree, every edge owns exactly one slot (self check), 0... }.
+ * Replaces nothing in the reference (numba walks CSR arrays, src/decoding/kernels.py:283-345); it is the
+ * data-layout step of qb_decoder_create, exposed for tests. */
+int qb_edge_layout_probe(int32_t m, int32_t n, const int32_t *indptr_h, const int32_t *indices_h,
+                         const double *prior_h, int32_t nwarps, int64_t *stats_out);
 void qb_decoder_destroy(qb_decoder *dec);
 
 /* ---- K3: batched flooding min-sum ------------------------------------------------------- */

@@ -39,7 +39,7 @@ class PipelineStats(C.Structure):
 
 EXPORTS = [
     "qb_last_error", "qb_device_count", "qb_version", "qb_decoder_create", "qb_decoder_set_prior",
-    "qb_decoder_destroy", "qb_minsum_batch", "qb_minsum_decode_host", "qb_minsum_core_host", "qb_alpha_messages_host", "qb_bp_decode_host",
+    "qb_decoder_destroy", "qb_edge_layout_probe", "qb_minsum_batch", "qb_minsum_decode_host", "qb_minsum_core_host", "qb_alpha_messages_host", "qb_bp_decode_host",
     "qb_syndrome_check_host", "qb_osd0_batch", "qb_osd0_host", "qb_gf2_eliminate_host", "qb_sampler_create",
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",

@@ -86,8 +86,9 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
     // a row of degree 1 (three unused slots in a one-chunk row) has no second edge: its min2 stays +inf
     float clip2 = clip;
     if constexpr (K == 1) clip2 = ((pads.y & 0xFFFFu) != 0xFFFFu) ? INFINITY : clip;
-    uint32_t a1 = __float_as_uint(alpha * fminf(m1, clip)) ^ tot;              // kernels.py:309-314
-    uint32_t a2 = __float_as_uint(alpha * fminf(m2, clip2)) ^ tot;
+    const float A1 = alpha * fminf(m1, clip), A2 = alpha * fminf(m2, clip2);  // kernels.py:309-314, A1 <= A2
+#ifndef QB_EDGE_SELECT_FMA
+    uint32_t a1 = __float_as_uint(A1) ^ tot, a2 = __float_as_uint(A2) ^ tot;
     asm volatile("" : "+r"(a1), "+r"(a2));                  // keep the multiplications out of the per-edge code
 #pragma unroll
     for (int c = 0; c < K; ++c) {
@@ -95,18 +96,35 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
         float r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            // sign(Q) is moved into bit 31 with two multiply-adds (fma pipe; the alu pipe is the busy one here):
-            // adding 2^31 to a word whose low 31 bits are untouched flips its sign bit
             const uint32_t sel = (fabsf(v[i]) == m1) ? a2 : a1;
-#ifndef QB_EDGE_IMAD_SIGN
             r[i] = __uint_as_float(sel ^ (__float_as_uint(v[i]) & 0x80000000u));
-#else
-            const uint32_t sb = __umulhi(__float_as_uint(v[i]), 2u);
-            r[i] = __uint_as_float(sb * 0x80000000u + sel);
-#endif
         }
         e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
     }
+#else
+    // Experiment kept for the record (measured 6 % slower on B200: the extra issue slots cost more than the alu pipe
+    // relief): the alu pipe (min/max, compares, selects, logic: half rate) bounds this phase, the fma pipe idles.  The
+    // magnitude |Q| == min1 ? A2 : A1 is therefore formed with multiply-adds:  t = |Q| - min1 is 0 exactly on the
+    // minimum edge(s) and >= 2^-149 elsewhere, t * 2^126 >= 2^-23, so  u = A2 - (t * 2^126) * 2^126  equals A2 on
+    // the minimum edge and is below -2^100 elsewhere, and max(u, A1) is the selected magnitude (A2 = +inf, the
+    // degree-1 row, included).  If every |Q| is +inf, t is NaN and max() returns A1 = A2.
+    float tsign = __uint_as_float(0x3F800000u | tot);       // +-1: total sign of the row
+    float nA2 = A2;
+    asm volatile("" : "+f"(tsign), "+f"(nA2));
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const float v[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float t = (fabsf(v[i]) - m1) * 8.507059e37f;                 // 2^126
+            const float u = fmaf(t, -8.507059e37f, nA2);
+            const float ks = fmaxf(u, A1) * tsign;
+            r[i] = __uint_as_float(__float_as_uint(ks) ^ (__float_as_uint(v[i]) & 0x80000000u));
+        }
+        e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+#endif
     // unused slots back to +inf (every row has at least one)
     E[pads.x & 0xFFFFu] = INFINITY;
     if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;

@@ -509,3 +509,62 @@ def test_run_simulation_alvarado_autoregressive_mode():
     res2 = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=1000, num_cycles=6, maxIter=6,
                           alpha_mode="alvarado", base_seed=3, alpha_estimation_trials=300, **s["bb"])
     assert 0.1 < res2["logical_error_rate"] < 0.8 and res2["alpha_r2_z"] is not None
+
+
+# ---- per-edge min-sum kernel vs the compressed-state kernel and the oracle on awkward graphs ---------------------------
+def test_edge_kernel_matches_compressed_state_kernel_and_oracle_on_random_graphs():
+    """The per-edge kernel (minsum_edge.cu) and the compressed-state kernel (minsum.cu) implement the same float32
+    recurrence: same hard decisions, convergence flags and iteration counts, posteriors equal up to the last bits
+    (different but fixed summation trees are not involved: both add in row order).  Graphs cover the generic paths:
+    column degree > 8, rows with more than 36 entries, empty rows and columns, degree-1 rows (+-inf messages), few
+    and many distinct priors, partial slices, set_prior re-layout."""
+    rng = np.random.default_rng(2024)
+    cases = []
+    H = (rng.random((60, 400)) < 0.06).astype(np.int8); H[5] = 0; H[:, 17] = 0
+    cases.append((H, np.full(400, 2.0)))                                         # uniform prior, empty row / column
+    cases.append((H, rng.choice([1.5, 2.5, -0.5, 4.0], 400)))                    # a few prior classes, one negative
+    cases.append((H, rng.normal(2.5, 1.0, 400)))                                 # per-lane priors
+    H2 = (rng.random((30, 120)) < 0.4).astype(np.int8)                           # row degree ~48 (> 9 chunks), column degree ~12
+    cases.append((H2, np.full(120, 1.0)))
+    H3 = np.zeros((40, 90), np.int8)
+    for r in range(30):
+        H3[r, rng.choice(80, 6, replace=False)] = 1
+    for r in range(30, 40):
+        H3[r, 80 + (r - 30)] = 1                                                  # degree-1 rows -> +-inf posteriors
+    H3[3, 85] = 1; H3[4, 85] = 1
+    cases.append((H3, np.full(90, 3.0)))
+    for H, prior in cases:
+        Hc = csr_matrix(H); m, n = H.shape
+        B = 64
+        e = (rng.random((B, n)) < 0.06).astype(np.int8)
+        syn = (e @ H.T % 2).astype(np.int8)
+        outs = []
+        for no_edge in ("", "1"):
+            if no_edge:
+                os.environ["QLDPC_B200_NO_EDGE"] = "1"
+            else:
+                os.environ.pop("QLDPC_B200_NO_EDGE", None)
+            try:
+                dec = _lib.Decoder(Hc.indptr, Hc.indices, n, prior)
+                outs.append(dec.minsum(syn, 12, _lib.QB_ALPHA_DYNAMIC))
+                if not no_edge:      # prior change -> the layout is rebuilt
+                    dec.set_prior(prior * 0.5)
+                    alt = dec.minsum(syn, 12, _lib.QB_ALPHA_DYNAMIC)
+                    dec.set_prior(prior)
+                    again = dec.minsum(syn, 12, _lib.QB_ALPHA_DYNAMIC)
+                    for a_, b_ in zip(again, outs[0]):
+                        assert np.array_equal(a_, b_, equal_nan=True)
+                    assert alt[0].shape == outs[0][0].shape
+                dec.close()
+            finally:
+                os.environ.pop("QLDPC_B200_NO_EDGE", None)
+        (h0, c0, v0, f0), (h1, c1, v1, f1) = outs
+        assert np.array_equal(c0, c1) and np.array_equal(f0, f1) and np.array_equal(h0, h1)
+        assert np.array_equal(np.isinf(v0), np.isinf(v1)) and np.array_equal(np.isnan(v0), np.isnan(v1))
+        fin_ = np.isfinite(v0)
+        np.testing.assert_allclose(v0[fin_], v1[fin_], rtol=1e-6, atol=1e-6)
+        for i in range(0, B, 8):      # and the float64 oracle (hard decisions of converged shots, flags)
+            oh, oc, ov, of = orc.performMinSum_Symmetric_Sparse(Hc, syn[i], prior, maxIter=12)
+            assert oc == c0[i] and of == f0[i]
+            if oc:
+                assert np.array_equal(oh, h0[i])
