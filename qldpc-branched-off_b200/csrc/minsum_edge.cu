@@ -174,6 +174,10 @@ template <bool FIRST>
 __device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
                                              uint32_t synsign, float alpha, float clip, uint2 pads)
 {
+#ifdef QB_EDGE_ROW_LOOP
+    row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, clip, pads);
+    return;
+#endif
     switch (K) {
     case 1: row_task<1, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
     case 2: row_task<2, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
@@ -230,7 +234,7 @@ __device__ __forceinline__ void load_idx_words(const ColCtx &c, int j, uint32_t 
     if constexpr (H & 1) w[H - 1] = lds_u32(base + (H / 2) * 256 + c.lane4);
 }
 
-// Groups of N consecutive slices of one class, software pipelined (see col_class).
+// gather addresses and gathered messages of a group of N slices
 template <int D, int N>
 struct ColGroup {
     uint32_t addr[N][D + 1];
@@ -317,25 +321,21 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
     c.ix += H * 128; c.sg += 32; c.t += 1;
 }
 
-// Software-pipelined groups of N consecutive slices of one class: the index words of group g+2 and the gathers
-// of group g+1 are in flight while group g is summed and scattered (the slots of different slices are disjoint).
+// Groups of N consecutive slices of one class (two slices at a time double the independent gathers in flight).
+// A software-pipelined version (gathers of the next group issued before the current one is scattered) was measured
+// slower on B200: the larger unrolled code costs more in instruction fetch than the extra overlap gains.
+#ifndef QB_EDGE_GROUP
+#define QB_EDGE_GROUP 1
+#endif
 template <int D, bool EXACT, bool WRITE_V>
 __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &pri)
 {
-    constexpr int N = (D <= 4) ? 2 : 1;
-    int ng = cnt / N;
-    if (ng > 0) {
+    constexpr int N = (D <= 4) ? QB_EDGE_GROUP : 1;
+    for (int ng = cnt / N; ng > 0; --ng) {
         uint32_t w[N][(D + 1) / 2 + 1];
-        ColGroup<D, N> G, G2;
+        ColGroup<D, N> G;
         group_load_idx<D, N>(c, 0, w);
         group_gather<D, N>(w, G);
-        group_load_idx<D, N>(c, 1, w);                     // may read past the class (never past the table region): unused then
-        for (; ng > 1; --ng) {
-            group_gather<D, N>(w, G2);
-            group_load_idx<D, N>(c, 2, w);
-            group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
-            G = G2;
-        }
         group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
     }
     if constexpr (N == 2) {
@@ -349,6 +349,9 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
     }
 }
 
+// The warp's column slices are sorted by class; cls holds the number of slices per class (16 x u8).  (A jump-table
+// dispatch over a per-warp class program and 2-slice / software-pipelined groups were all measured slower: this
+// phase is sensitive to instruction-fetch stalls, the smallest code wins.)
 template <bool WRITE_V>
 __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, const uint32_t *cmeta, const float *lane_prior, const EdgePriors &pri)
 {
@@ -450,6 +453,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
     const int r0 = eg.wr_ptr[warp], r1 = eg.wr_ptr[warp + 1];
     const int c0 = eg.wc_ptr[warp];
     const uint4 cls = eg.wc_cls[warp];
+
     const int c1 = eg.wc_ptr[warp + 1];
     // shared address of the index block of the warp's first column slice
     const uint32_t ix0 = idx_addr + (c0 < eg.n_csl ? (eg.ctask[c0].x & 0xFFFFu) * 128u : 0u);
