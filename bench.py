@@ -63,9 +63,11 @@ def summarize_clocks(lines):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one minsum_fast_kernel launch, from the `ncu --set full` capture of
-# this command (profiles/r1_ncu_full_final_summary.txt): 0.0216 GB + 2.2022 GB for a 65536-shot launch.
-NCU_TRAFFIC_BYTES = {65536: 2.2238e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of one minsum_edge_kernel launch, from the `ncu --set full` capture of
+# `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --shots-per-step 16384 --batch 16384`
+# (profiles/r1b_ncu_full_summary.txt): 4.3 MB + 508.8 MB for a 16384-shot launch = 31.3 KB per shot (the posteriors of the
+# non-converged sides, 0.946 x 8857 x 4 B, dominate: no re-reads), scaled to the launch size.
+NCU_TRAFFIC_BYTES_PER_SHOT = (4.26e6 + 508.84e6) / 16384
 
 
 def measured_peaks():
@@ -250,7 +252,7 @@ def main():
         hbm_peak, peak_src = measured_peaks()
         total_shots = world * B * args.steps
         value = total_shots / (ms_max * 1e-3)
-        # dominant kernel: minsum_fast_kernel (two launches per batch: Z and X side)
+        # dominant kernel: minsum_edge_kernel (two launches per batch: Z and X side)
         n_ms_launch = 2 * agg["batches"]
         ms_launch = agg["ms_minsum"] / max(1, n_ms_launch)
         shots_per_launch = min(args.batch, B)
@@ -272,14 +274,15 @@ def main():
             "config": {"workload": WORKLOAD, "shots_per_step_per_gpu": B, "batch": args.batch, "max_iter": MAX_ITER,
                        "sampler": "Philox4x32-10 on device, counter = global shot index",
                        "l2": "no flush needed: per-batch posterior/state buffers (>1 GB) exceed the 126 MB L2 and every step decodes new shots"},
-            "roofline": {"bound": "hbm", "kernel": "minsum_fast_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(shots_per_launch), "traffic_unit": "bytes/launch (ncu, profiles/)",
+            "roofline": {"bound": "hbm", "kernel": "minsum_edge_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_SHOT * shots_per_launch, "traffic_unit": "bytes/launch (ncu dram read+write of a 16384-shot launch, scaled per shot; profiles/)",
                          "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
                          "ms_per_launch": ms_launch, "shots_per_launch": shots_per_launch,
                          "note": "HBM is not the binding resource by design (messages stay in shared memory); see roofline_smem"},
-            "roofline_smem": {"bound": "smem", "kernel": "minsum_fast_kernel", "edge_messages_per_s": em_per_s,
+            "roofline_smem": {"bound": "smem", "kernel": "minsum_edge_kernel", "edge_messages_per_s": em_per_s,
                               "achieved": em_per_s * 8 / 1e9, "peak": smem_peak, "unit": "GB/s", "frac": em_per_s * 8 / 1e9 / smem_peak,
-                              "bytes_per_edge_message": 8, "peak_source": "148 SMs x 128 B/clk x median SM clock under load"},
+                              "bytes_per_edge_message": 8, "peak_source": "148 SMs x 128 B/clk x median SM clock under load",
+                              "note": "SURVEY 8(d) algorithmic 8 B per edge-message; the kernel moves 16 B (two 4-byte gathers/scatters + the row-side LDS.128/STS.128) plus 2 B of slot index per edge-message, and is bound by the alu pipe (check rows) and by shared-memory instruction issue (variables), see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "shots_per_step": Be, "steps": e2e_steps,
                     "path": "qb_pipeline_run_events_host: host-sampled fault events (pinned) -> H2D -> K2 -> min-sum -> OSD-0 -> logical check -> flags D2H"},

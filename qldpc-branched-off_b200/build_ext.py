@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     keep = set(objs)
     for f in os.listdir(OBJDIR):     # drop objects of much older source revisions
         p = os.path.join(OBJDIR, f)
-        if p not in keep and os.path.getmtime(p) < os.path.getmtime(OUT) - 7200:
+        if p not in keep and os.path.getmtime(p) < os.path.getmtime(OUT) - 900:
             os.remove(p)
     return OUT
 

@@ -353,7 +353,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
 // dispatch over a per-warp class program and 2-slice / software-pipelined groups were all measured slower: this
 // phase is sensitive to instruction-fetch stalls, the smallest code wins.)
 template <bool WRITE_V>
-__device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, const uint32_t *cmeta, const float *lane_prior, const EdgePriors &pri)
+__device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, int t_end, const uint32_t *cmeta, const float *lane_prior, const EdgePriors &pri)
 {
     col_class<0, false, WRITE_V>(c, cls.x & 255, pri);
     col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255, pri);
@@ -362,6 +362,7 @@ __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, const uint32_t *cm
     col_class<4, false, WRITE_V>(c, cls.y & 255, pri);
     col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255, pri);
     col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255, pri);
+    if (c.t >= t_end) return;                              // the rare classes follow: skip their tests (far jumps)
     col_class<7, false, WRITE_V>(c, cls.y >> 24, pri);
     col_class<8, false, WRITE_V>(c, cls.z & 255, pri);
     col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255, pri);
@@ -515,8 +516,8 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.vid = eg.var_id + c0 * 32 + lane;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
 #ifndef QB_EDGE_SKIP_B
-            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, cmeta, eg.lane_prior, pri);
-            else phase_b<false>(c, cls, cmeta, eg.lane_prior, pri);
+            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            else phase_b<false>(c, cls, c1, cmeta, eg.lane_prior, pri);
 #endif
             if (lane < c1 - c0) hperm[c0 + lane] = c.myhw;
             const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp);
