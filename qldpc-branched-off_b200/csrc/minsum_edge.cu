@@ -214,7 +214,8 @@ struct ColCtx {
     uint32_t sg;            // shared address of the 8-bit fingerprint of the next task's lane variable
     uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
     uint32_t myhw;          // lane j keeps the hard-decision word of the warp's j-th task
-    int t, t0;              // next task, first task of the warp
+    uint32_t t4;            // 4 * next task: byte offset of its prior, compared with lane_t4 to pick the lane that keeps its hard-decision word
+    uint32_t lane_t4;       // 4 * (first task of the warp + lane)
     int lane;
     const uint16_t *vid;    // next task's variable id of the lane (posterior output)
     float *post;            // posterior row of the shot
@@ -270,7 +271,7 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
         float acc = D > 0 ? G.r[j][0] : 0.f;               // kernels.py:316 (row order)
 #pragma unroll
         for (int k = 1; k < D; ++k) acc += G.r[j][k];
-        v[j] = acc + __uint_as_float(pri.bits[c.t + j]);   // kernels.py:320
+        v[j] = acc + __uint_as_float(*reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pri.bits) + c.t4 + 4 * j));   // kernels.py:320
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -285,11 +286,11 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
         const bool neg = v[j] < 0.f;                       // kernels.py:349
         if (neg) c.fp ^= lds_u8(c.sg + 32 * j);
         const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-        if (c.lane == c.t + j - c.t0) c.myhw = hw;
+        if (c.lane_t4 == c.t4 + 4 * j) c.myhw = hw;
         if constexpr (WRITE_V) { const uint32_t vid = c.vid[32 * j]; if (vid != 0xFFFFu) c.post[vid] = v[j]; }
     }
     if constexpr (WRITE_V) c.vid += 32 * N;
-    c.ix += N * ((D + 1) / 2) * 128; c.sg += 32 * N; c.t += N;
+    c.ix += N * ((D + 1) / 2) * 128; c.sg += 32 * N; c.t4 += 4 * N;
 }
 
 // any slice: partial with a negative prior, per-lane priors, large degree (meta = degree << 16 | lanes << 22)
@@ -304,7 +305,7 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
             const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
             acc += lds_f32((k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu));
         }
-        const float v = acc + (lane_prior ? __ldg(lane_prior) : __uint_as_float(pri.bits[c.t]));
+        const float v = acc + (lane_prior ? __ldg(lane_prior) : __uint_as_float(pri.bits[c.t4 >> 2]));
         for (int k = 0; k < D; ++k) {
             const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
             const uint32_t addr = (k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu);
@@ -316,9 +317,9 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
         if (WRITE_V) c.post[*c.vid] = v;
     }
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-    if (c.lane == c.t - c.t0) c.myhw = hw;
+    if (c.lane_t4 == c.t4) c.myhw = hw;
     if (WRITE_V) c.vid += 32;
-    c.ix += H * 128; c.sg += 32; c.t += 1;
+    c.ix += H * 128; c.sg += 32; c.t4 += 4;
 }
 
 // Groups of N consecutive slices of one class (two slices at a time double the independent gathers in flight).
@@ -331,7 +332,9 @@ template <int D, bool EXACT, bool WRITE_V>
 __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &pri)
 {
     constexpr int N = (D <= 4) ? QB_EDGE_GROUP : 1;
-    for (int ng = cnt / N; ng > 0; --ng) {
+    const uint32_t t4_end = c.t4 + 4u * (uint32_t)(cnt / N * N);
+#pragma unroll 1
+    while (c.t4 != t4_end) {
         uint32_t w[N][(D + 1) / 2 + 1];
         ColGroup<D, N> G;
         group_load_idx<D, N>(c, 0, w);
@@ -362,7 +365,7 @@ __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, int t_end, const u
     col_class<4, false, WRITE_V>(c, cls.y & 255, pri);
     col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255, pri);
     col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255, pri);
-    if (c.t >= t_end) return;                              // the rare classes follow: skip their tests (far jumps)
+    if (c.t4 >= 4u * (uint32_t)t_end) return;              // the rare classes follow: skip their tests (far jumps)
     col_class<7, false, WRITE_V>(c, cls.y >> 24, pri);
     col_class<8, false, WRITE_V>(c, cls.z & 255, pri);
     col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255, pri);
@@ -373,7 +376,7 @@ __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, int t_end, const u
     col_class<6, true, WRITE_V>(c, (cls.w >> 16) & 255, pri);
     const int ngen = cls.w >> 24;
     for (int i = 0; i < ngen; ++i)
-        col_task_generic<WRITE_V>(c, cmeta[c.t], lane_prior ? lane_prior + c.t * 32 + c.lane : nullptr, pri);
+        col_task_generic<WRITE_V>(c, cmeta[c.t4 >> 2], lane_prior ? lane_prior + (c.t4 >> 2) * 32 + c.lane : nullptr, pri);
 }
 
 // weight of the residual syndrome par ^ syn (0 = converged); resets par.  Called by warp 0 only.
@@ -512,7 +515,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.lane4 = lane * 4; c.lane8 = lane * 8;
             c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
             c.fp = 0u; c.myhw = 0u;
-            c.t = c0; c.t0 = c0; c.lane = lane;
+            c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
 #ifndef QB_EDGE_SKIP_B
