@@ -293,7 +293,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     }
     L.col_sig.assign((size_t)L.n_csl * 32, 0u);
     L.ctask.assign((size_t)L.n_csl * 2, 0u);
-    L.var_id.assign((size_t)L.n_csl * 32, 0xFFFFu);
+    L.var_id.assign((size_t)(L.n_csl + 1) * 32, 0xFFFFu);      // one slice of padding: the kernel reads one slice ahead
     if (!L.uniform_prior) L.lane_prior.assign((size_t)L.n_csl * 32, 0.f);
     int iw = 0;
     std::vector<int> cs_base(L.n_csl);

@@ -218,6 +218,7 @@ struct ColCtx {
     uint32_t lane_t4;       // 4 * (first task of the warp + lane)
     int lane;
     const uint16_t *vid;    // next task's variable id of the lane (posterior output)
+    uint32_t vid_next;      // its value, loaded one task ahead
     float *post;            // posterior row of the shot
 };
 
@@ -287,9 +288,14 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
         if (neg) c.fp ^= lds_u8(c.sg + 32 * j);
         const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
         if (c.lane_t4 == c.t4 + 4 * j) c.myhw = hw;
-        if constexpr (WRITE_V) { const uint32_t vid = c.vid[32 * j]; if (vid != 0xFFFFu) c.post[vid] = v[j]; }
+        if constexpr (WRITE_V) {
+            static_assert(N == 1, "posterior output assumes one slice per group");
+            const uint32_t vid = c.vid_next;                // loaded one task ahead: the store does not wait on it
+            c.vid += 32;
+            c.vid_next = __ldg(c.vid);                      // (the table is padded by one slice)
+            if (vid != 0xFFFFu) c.post[vid] = v[j];
+        }
     }
-    if constexpr (WRITE_V) c.vid += 32 * N;
     c.ix += N * ((D + 1) / 2) * 128; c.sg += 32 * N; c.t4 += 4 * N;
 }
 
@@ -314,11 +320,11 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
         }
         neg = v < 0.f;
         if (neg) c.fp ^= lds_u8(c.sg);
-        if (WRITE_V) c.post[*c.vid] = v;
+        if (WRITE_V) c.post[c.vid_next] = v;
     }
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
     if (c.lane_t4 == c.t4) c.myhw = hw;
-    if (WRITE_V) c.vid += 32;
+    if (WRITE_V) { c.vid += 32; c.vid_next = __ldg(c.vid); }
     c.ix += H * 128; c.sg += 32; c.t4 += 4;
 }
 
@@ -387,22 +393,53 @@ __device__ __forceinline__ int residual_weight(uint32_t *par, const uint32_t *sy
     return __reduce_add_sync(0xFFFFFFFFu, wt);
 }
 
-// exact H.hard for the hard decision in hperm: par ^= rows of every variable whose bit is set (all threads; par must be 0)
-__device__ __forceinline__ void parity_of_hard(const EdgeDev &eg, const uint32_t *hperm, uint32_t *par, int tid, int nthreads)
+// exact H.hard for the hard decision in hperm: par ^= rows of every variable whose bit is set (all threads; par must
+// be 0; contains barriers).  The set bits are first compacted into a list so that every (variable, edge) pair gets
+// its own thread: the row positions come from global memory and the loads of one thread would otherwise serialise.
+constexpr int PAR_LIST_CAP = 512;
+__device__ __forceinline__ void parity_of_hard(const EdgeDev &eg, const uint32_t *hperm, const uint32_t *cmeta, uint32_t *par,
+                                               uint16_t *list, int *list_count, int tid, int nthreads)
 {
+    if (tid == 0) *list_count = 0;
+    __syncthreads();
     for (int t = tid; t < eg.n_csl; t += nthreads) {
         uint32_t bits = hperm[t];
-        if (!bits) continue;
-        const uint32_t dx = __ldg(&eg.ctask[t]).x;
-        const int D = (dx >> 16) & 63, H = (D + 1) >> 1;
-        const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            for (int k = 0; k < D; ++k) {
+            const int slot = atomicAdd(list_count, 1);
+            if (slot < PAR_LIST_CAP) list[slot] = (uint16_t)(t * 32 + b);
+        }
+    }
+    __syncthreads();
+    const int cnt = *list_count;
+    if (cnt <= PAR_LIST_CAP) {
+        for (int i = tid; i < cnt * 8; i += nthreads) {              // degree <= 16: two passes of 8 edges
+            const int e = list[i >> 3], t = e >> 5, b = e & 31;
+            const uint32_t dx = cmeta[t];
+            const int D = (dx >> 16) & 63, H = (D + 1) >> 1;
+            const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
+            for (int k = i & 7; k < D; k += 8) {
                 const uint32_t w = __ldg(&rp[edge_idx_off(H, k >> 1, b)]);
                 const uint32_t pos = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
                 atomicXor(&par[pos >> 5], 1u << (pos & 31));
+            }
+        }
+    } else {
+        for (int t = tid; t < eg.n_csl; t += nthreads) {
+            uint32_t bits = hperm[t];
+            if (!bits) continue;
+            const uint32_t dx = cmeta[t];
+            const int D = (dx >> 16) & 63, H = (D + 1) >> 1;
+            const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                for (int k = 0; k < D; ++k) {
+                    const uint32_t w = __ldg(&rp[edge_idx_off(H, k >> 1, b)]);
+                    const uint32_t pos = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+                    atomicXor(&par[pos >> 5], 1u << (pos & 31));
+                }
             }
         }
     }
@@ -436,7 +473,9 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
     uint32_t *hnat = hperm + eg.n_csl;                                                // [nw] hard decision, natural order
     uint32_t *cmeta = hnat + eg.nw;                                                   // [n_csl] degree / lanes of every column slice
     uint8_t *csig = reinterpret_cast<uint8_t *>(cmeta + eg.n_csl);                    // [n_csl*32] 8-bit fingerprint per variable
-    __shared__ int s_wt, s_next;
+    __shared__ int s_wt, s_next, s_pcount;
+    __shared__ uint16_t s_plist[PAR_LIST_CAP];
+    __shared__ float s_alpha[128];                                                    // alpha schedule (first 128 iterations)
     __shared__ uint32_t s_fp[2], s_target;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -452,6 +491,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
         hperm[i] = 0u;
     }
     for (int i = tid; i < eg.n_rsl; i += THREADS) rtask[i] = eg.rtask[i];
+    for (int i = tid; i < 128 && i < a.max_iter; i += THREADS) s_alpha[i] = a.alpha_d[i];
     for (int i = tid; i < eg.n_csl * 32; i += THREADS) csig[i] = (uint8_t)eg.col_sig[i];
     if (tid < 32) E[eg.e_dummy + tid] = 0.f;                                         // dummy lanes of partial column slices
     const int r0 = eg.wr_ptr[warp], r1 = eg.wr_ptr[warp + 1];
@@ -491,7 +531,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
         int fin = a.max_iter - 1, wt = 0;
         for (int it = 0; it < a.max_iter; ++it) {
             // ---- phase A --------------------------------------------------------------------------------
-            const float alpha = a.alpha_d[it];
+            const float alpha = it < 128 ? s_alpha[it] : a.alpha_d[it];
             PROF_T(t0);
 #ifndef QB_EDGE_SKIP_A
             for (int t = r0; t < r1; ++t) {
@@ -510,6 +550,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             PROF_BLOCK();
             PROF_T(t2);
             // ---- phase B --------------------------------------------------------------------------------
+            const bool write_v = a.post && (api || it == a.max_iter - 1);
             ColCtx c;
             c.ix = ix0;
             c.lane4 = lane * 4; c.lane8 = lane * 8;
@@ -517,9 +558,10 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.fp = 0u; c.myhw = 0u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
+            c.vid_next = write_v ? __ldg(c.vid) : 0u;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
 #ifndef QB_EDGE_SKIP_B
-            if (a.post && (api || it == a.max_iter - 1)) phase_b<true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            if (write_v) phase_b<true>(c, cls, c1, cmeta, eg.lane_prior, pri);
             else phase_b<false>(c, cls, c1, cmeta, eg.lane_prior, pri);
 #endif
             if (lane < c1 - c0) hperm[c0 + lane] = c.myhw;
@@ -532,7 +574,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             PROF_ADD(0, t1 - t0); PROF_ADD(1, t2 - t1); PROF_ADD(2, t3 - t2); PROF_ADD(3, t4 - t3);
             // ---- convergence: fingerprint of H.hard against the syndrome's, exact test only on a match -----
             if (s_fp[it & 1] == target) {                                              // uniform
-                parity_of_hard(eg, hperm, par, tid, THREADS);
+                parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
                 __syncthreads();
                 if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
                 __syncthreads();
@@ -540,7 +582,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             }
         }
         if (!conv && a.max_iter > 0 && a.fail_wt) {                                    // weight of the residual syndrome (OSD scheduling hint)
-            parity_of_hard(eg, hperm, par, tid, THREADS);
+            parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
             __syncthreads();
             if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
             __syncthreads();
@@ -639,9 +681,9 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     EdgeLayout L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
     if (!L.ok || L.n_csl > EDGE_MAX_CSL) return QB_OK;
     size_t smem = edge_smem_bytes(L, g.nw);
-    if (smem > limit) return QB_OK;
+    if (smem + 2048 > limit) return QB_OK;             // 2 KB: the kernel's static shared memory
     // several CTAs per SM for small codes: fewer warps each
-    int ctas = (int)std::min<size_t>(4, (limit + 1024) / (smem + 1024));
+    int ctas = (int)std::min<size_t>(4, (limit + 1024) / (smem + 2048 + 1024));
     if (const char *e = getenv("QLDPC_B200_EDGE_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));
     int want = ctas >= 4 ? 8 : (ctas >= 2 ? 16 : 32);
     if (const char *e = getenv("QLDPC_B200_EDGE_WARPS")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) want = w; }
@@ -650,7 +692,7 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
         L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
         if (!L.ok) return QB_OK;
         smem = edge_smem_bytes(L, g.nw);
-        if (smem > limit) return QB_OK;
+        if (smem + 2048 > limit) return QB_OK;             // 2 KB: the kernel's static shared memory
     }
     EdgePlan *p = new EdgePlan();
     p->threads = nwarps * 32; p->ctas_per_sm = ctas; p->smem = smem;

@@ -6,7 +6,7 @@
 using namespace qb;
 
 template <int MODE>
-__global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_per_warp, int D, int a_warps = 0, int a_tasks = 0)
+__global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_per_warp, int D, int a_warps, int a_tasks, const __grid_constant__ EdgePriors pri)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e_words = (MODE >= 2) ? 34000 : 24000;
@@ -17,8 +17,7 @@ __global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_p
     const int nwarps = blockDim.x >> 5;
     const int H = (D + 1) / 2;
     const int n_csl = (nwarps - a_warps) * tasks_per_warp;
-    uint32_t *ptab = idx + n_csl * H * 32;
-    uint32_t *cmeta = ptab + 2 * n_csl;
+    uint32_t *cmeta = idx + n_csl * H * 32;
     uint8_t *csig = reinterpret_cast<uint8_t *>(cmeta + n_csl);
     const uint32_t e_word = (uint32_t)__cvta_generic_to_shared(E) >> 2;
     for (int i = tid; i < e_words; i += blockDim.x) E[i] = 0.001f * (i & 1023);
@@ -31,12 +30,12 @@ __global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_p
                 const uint32_t row = (uint32_t)((t * 131 + k * 977 + l * 37 + 11) % 740);
                 s[h] = row * 32 + ((l * 5 + k + t) & 31) + e_word;
             }
-            idx[(t * H + kk) * 32 + l] = s[0] | (s[1] << 16);
+            idx[t * H * 32 + edge_idx_off(H, kk, l)] = s[0] | (s[1] << 16);
         }
-    for (int i = tid; i < n_csl; i += blockDim.x) { ptab[2 * i] = __float_as_uint(3.0f); ptab[2 * i + 1] = 0; cmeta[i] = 0; }
+    for (int i = tid; i < n_csl; i += blockDim.x) cmeta[i] = 0;
     for (int i = tid; i < n_csl * 32; i += blockDim.x) csig[i] = (uint8_t)i;
     __syncthreads();
-    const uint32_t idx_addr = (uint32_t)__cvta_generic_to_shared(idx), ptab_addr = (uint32_t)__cvta_generic_to_shared(ptab);
+    const uint32_t idx_addr = (uint32_t)__cvta_generic_to_shared(idx);
     const int c0 = warp * tasks_per_warp;
     uint4 cls = make_uint4(0, 0, 0, 0);
     if (D == 2) cls.x = tasks_per_warp << 16;
@@ -58,12 +57,11 @@ __global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_p
                     }
             } else if (MODE != 3) {
                 ColCtx c;
-                c.ix = idx_addr + cb * H * 128 + lane * 4;
-                c.pt = ptab_addr + cb * 8;
+                c.ix = idx_addr + cb * H * 128; c.lane4 = lane * 4; c.lane8 = lane * 8;
                 c.sg = (uint32_t)__cvta_generic_to_shared(csig + cb * 32 + lane);
-                c.fp = 0u; c.vid = nullptr; c.post = nullptr; c.lane0 = lane == 0;
-                phase_b<false>(c, cls, cmeta, ptab_addr, nullptr, lane);
-                fpacc ^= c.fp;
+                c.fp = 0u; c.myhw = 0u; c.t4 = 4u * cb; c.lane_t4 = 4u * (cb + lane); c.lane = lane; c.vid = nullptr; c.post = nullptr;
+                phase_b<false>(c, cls, cb + tasks_per_warp, cmeta, nullptr, pri);
+                fpacc ^= c.fp ^ c.myhw;
             }
             __syncthreads();
         }
@@ -72,12 +70,11 @@ __global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_p
     }
     for (int it = 0; it < iters; ++it) {
         ColCtx c;
-        c.ix = idx_addr + c0 * H * 128 + lane * 4;
-        c.pt = ptab_addr + c0 * 8;
+        c.ix = idx_addr + c0 * H * 128; c.lane4 = lane * 4; c.lane8 = lane * 8;
         c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
-        c.fp = 0u; c.vid = nullptr; c.post = nullptr; c.lane0 = lane == 0;
-        phase_b<false>(c, cls, cmeta, ptab_addr, nullptr, lane);
-        fpacc ^= c.fp;
+        c.fp = 0u; c.myhw = 0u; c.t4 = 4u * c0; c.lane_t4 = 4u * (c0 + lane); c.lane = lane; c.vid = nullptr; c.post = nullptr;
+        phase_b<false>(c, cls, c0 + tasks_per_warp, cmeta, nullptr, pri);
+        fpacc ^= c.fp ^ c.myhw;
         if (MODE == 0) __syncthreads();
     }
     out[blockIdx.x * blockDim.x + tid] = E[tid] + fpacc;
@@ -86,6 +83,7 @@ __global__ void __launch_bounds__(1024, 1) kb(float *out, int iters, int tasks_p
 int main()
 {
     float *out; cudaMalloc(&out, 148 * 1024 * 4);
+    EdgePriors pri; for (int i = 0; i < EDGE_MAX_CSL; ++i) pri.bits[i] = 0x40400000u;   // 3.0f
     const int iters = 2000;
     for (int mode = 0; mode < 2; ++mode)
         for (int threads : {1024, 512})
@@ -94,9 +92,9 @@ int main()
                 auto fn = mode == 0 ? kb<0> : kb<1>;
                 cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220000);
                 cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-                fn<<<148, threads, 220000>>>(out, 10, tpw, D, 0, 0);
+                fn<<<148, threads, 220000>>>(out, 10, tpw, D, 0, 0, pri);
                 cudaEventRecord(e0);
-                fn<<<148, threads, 220000>>>(out, iters, tpw, D, 0, 0);
+                fn<<<148, threads, 220000>>>(out, iters, tpw, D, 0, 0, pri);
                 cudaEventRecord(e1);
                 cudaDeviceSynchronize();
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -110,14 +108,27 @@ int main()
         auto fn = mode == 2 ? kb<2> : mode == 3 ? kb<3> : kb<4>;
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225000);
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        fn<<<148, 1024, 225000>>>(out, 10, 12, 3, 8, 5);
+        fn<<<148, 1024, 225000>>>(out, 10, 12, 3, 8, 5, pri);
         cudaEventRecord(e0);
-        fn<<<148, 1024, 225000>>>(out, iters, 12, 3, 8, 5);
+        fn<<<148, 1024, 225000>>>(out, iters, 12, 3, 8, 5, pri);
         cudaEventRecord(e1);
         cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         printf("%s: %.0f cycles per iteration (%s)\n", mode == 2 ? "A (8 warps x 5 row tasks) || B (24 warps x 12 tasks)" : mode == 3 ? "A only (8 warps x 5 row tasks)" : "B only (24 warps x 12 tasks)",
                ms * 1e-3 * 1.965e9 / iters, cudaGetErrorString(cudaGetLastError()));
+    }
+    // check-row phase alone in the real kernel's shape: 25 warps x 1 row task (K = 9), 7 idle warps
+    for (int aw : {25, 28, 32}) {
+        auto fn = kb<3>;
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225000);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        fn<<<148, 1024, 225000>>>(out, 10, 1, 3, aw, 1, pri);
+        cudaEventRecord(e0);
+        fn<<<148, 1024, 225000>>>(out, iters, 1, 3, aw, 1, pri);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("A only: %d warps x 1 row task (K=9): %.0f cycles per iteration (%s)\n", aw, ms * 1e-3 * 1.965e9 / iters, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
