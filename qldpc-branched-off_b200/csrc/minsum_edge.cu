@@ -509,14 +509,25 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
     unsigned long long prof[4] = {0, 0, 0, 0};
 #endif
 
+    // row id and fingerprint mask of the lane's row in the warp's first two row slices (static: kept in registers so
+    // that the per-shot syndrome load is one global round trip)
+    uint32_t rid_c[2], msk_c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int t = warp + u * (THREADS / 32);
+        rid_c[u] = t < eg.n_rsl ? eg.row_id[t * 32 + lane] : 0xFFFFu;
+        msk_c[u] = t < eg.n_rsl ? (eg.row_mask[t * 32 + lane] & 0xFFu) : 0u;
+    }
+
     while (shot < a.B) {                                                              // uniform
         // ---- load: permuted syndrome words and their fingerprint, parity = 0 ----------------------------------
         {
             uint32_t tg = 0u;
-            for (int t = warp; t < eg.n_rsl; t += THREADS / 32) {
-                const uint32_t rid = eg.row_id[t * 32 + lane];
+            int u = 0;
+            for (int t = warp; t < eg.n_rsl; t += THREADS / 32, ++u) {
+                const uint32_t rid = u == 0 ? rid_c[0] : (u == 1 ? rid_c[1] : (uint32_t)eg.row_id[t * 32 + lane]);
                 const bool bit = rid != 0xFFFFu && ((a.syn_bits[(size_t)shot * eg.mw + (rid >> 5)] >> (rid & 31)) & 1u);
-                if (bit) tg ^= eg.row_mask[t * 32 + lane] & 0xFFu;
+                if (bit) tg ^= u == 0 ? msk_c[0] : (u == 1 ? msk_c[1] : (eg.row_mask[t * 32 + lane] & 0xFFu));
                 const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
                 if (lane == 0) { syn[t] = word; par[t] = 0u; }
             }
@@ -603,17 +614,20 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
         }
         __syncthreads();
         for (int w = tid; w < eg.nw; w += THREADS) a.hard_bits[(size_t)shot * eg.nw + w] = hnat[w];
-        if (tid == 0) {
-            a.converged[shot] = conv ? 1 : 0;
-            a.final_iter[shot] = fin;
+        const int done_shot = shot;
+        shot = s_next;
+        __syncthreads();
+        // bookkeeping of the finished shot after the barrier: the round trip of the queue atomic overlaps the next
+        // shot's syndrome load instead of holding all warps at the barrier
+        if (tid == THREADS - 1) {
+            a.converged[done_shot] = conv ? 1 : 0;
+            a.final_iter[done_shot] = fin;
             if (!conv && a.fail_count) {
                 const int slot = atomicAdd(a.fail_count, 1);
-                a.fail_idx[slot] = shot;
+                a.fail_idx[slot] = done_shot;
                 if (a.fail_wt) a.fail_wt[slot] = wt;
             }
         }
-        shot = s_next;
-        __syncthreads();
     }
 #ifdef QB_EDGE_PROFILE
     if (lane == 0 && blockIdx.x < 256)
