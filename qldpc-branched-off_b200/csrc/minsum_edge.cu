@@ -7,13 +7,14 @@
 //            Between phase B and phase A it holds the variable-to-check message Q (kernels.py:323-345),
 //            between phase A and phase B the check-to-variable message R (kernels.py:283-316).
 //   phase A  one lane per check row: stream the row's Q with LDS.128, keep them in registers, reduce
-//            (min1 with the sign product in ONE instruction: min.xorsign.abs; min2 with two FMNMX), then
-//            R = sign * alpha * (|Q| == min1 ? min2 : min1) written back in place (STS.128).  The value test
-//            replaces the reference's argmin position: when two edges tie for min1, min2 == min1.
+//            (min1 with the sign product in ONE instruction: min.xorsign.abs; min2 with FMNMX + a 3-input FMNMX3
+//            per two edges), then R = sign * alpha * (|Q| == min1 ? min2 : min1) written back in place (STS.128).
+//            The value test replaces the reference's argmin position: when two edges tie for min1, min2 == min1.
+//            The clip of kernels.py:330-333 is applied here, once per row, to min1 / min2 (E holds unclipped Q).
 //   phase B  one lane per variable: gather its <= 16 R through precomputed 16-bit slot indices (bank
 //            conflict free by construction), sum in row order + prior (kernels.py:316-320), hard decision,
-//            Q = clip(v - R) (NaN -> 0 first, kernels.py:327-333) scattered back to the same slots.
-//            Convergence (H.hard == syndrome, kernels.py:352-364) is first tested on a 32-bit linear fingerprint
+//            Q = v - R (NaN -> 0 next to degree-1 rows, kernels.py:327-329) scattered back to the same slots.
+//            Convergence (H.hard == syndrome, kernels.py:352-364) is first tested on an 8-bit linear fingerprint
 //            (XOR of per-column random signatures over the variables whose hard decision is 1 against the
 //            XOR of per-row masks over the syndrome) and confirmed exactly only when the fingerprints agree,
 //            so the common non-converged iteration never walks the graph a second time.
@@ -87,7 +88,10 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
     float clip2 = clip;
     if constexpr (K == 1) clip2 = ((pads.y & 0xFFFFu) != 0xFFFFu) ? INFINITY : clip;
     const float A1 = alpha * fminf(m1, clip), A2 = alpha * fminf(m2, clip2);  // kernels.py:309-314, A1 <= A2
-#ifndef QB_EDGE_SELECT_FMA
+    // Measured alternatives that lost (B200): forming the magnitude on the idle fma pipe (t = |Q| - min1 scaled to
+    // -inf unless 0, max(A2 + t, A1)): 6 % slower, the extra issue slots cost more than the alu-pipe relief; moving
+    // sign(Q) into bit 31 with IMAD.HI + IMAD instead of LOP3: 3 % slower; a two-pass loop over chunks instead of
+    // the fully unrolled row: 5 % slower.
     uint32_t a1 = __float_as_uint(A1) ^ tot, a2 = __float_as_uint(A2) ^ tot;
     asm volatile("" : "+r"(a1), "+r"(a2));                  // keep the multiplications out of the per-edge code
 #pragma unroll
@@ -101,30 +105,6 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
         }
         e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
     }
-#else
-    // Experiment kept for the record (measured 6 % slower on B200: the extra issue slots cost more than the alu pipe
-    // relief): the alu pipe (min/max, compares, selects, logic: half rate) bounds this phase, the fma pipe idles.  The
-    // magnitude |Q| == min1 ? A2 : A1 is therefore formed with multiply-adds:  t = |Q| - min1 is 0 exactly on the
-    // minimum edge(s) and >= 2^-149 elsewhere, t * 2^126 >= 2^-23, so  u = A2 - (t * 2^126) * 2^126  equals A2 on
-    // the minimum edge and is below -2^100 elsewhere, and max(u, A1) is the selected magnitude (A2 = +inf, the
-    // degree-1 row, included).  If every |Q| is +inf, t is NaN and max() returns A1 = A2.
-    float tsign = __uint_as_float(0x3F800000u | tot);       // +-1: total sign of the row
-    float nA2 = A2;
-    asm volatile("" : "+f"(tsign), "+f"(nA2));
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-        const float v[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-        float r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float t = (fabsf(v[i]) - m1) * 8.507059e37f;                 // 2^126
-            const float u = fmaf(t, -8.507059e37f, nA2);
-            const float ks = fmaxf(u, A1) * tsign;
-            r[i] = __uint_as_float(__float_as_uint(ks) ^ (__float_as_uint(v[i]) & 0x80000000u));
-        }
-        e4[c * stride] = make_float4(r[0], r[1], r[2], r[3]);
-    }
-#endif
     // unused slots back to +inf (every row has at least one)
     E[pads.x & 0xFFFFu] = INFINITY;
     if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;
@@ -174,10 +154,6 @@ template <bool FIRST>
 __device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
                                              uint32_t synsign, float alpha, float clip, uint2 pads)
 {
-#ifdef QB_EDGE_ROW_LOOP
-    row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, clip, pads);
-    return;
-#endif
     switch (K) {
     case 1: row_task<1, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
     case 2: row_task<2, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
