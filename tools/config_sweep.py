@@ -13,6 +13,9 @@ from qldpc_b200.simulation.engine import ShotEngine
 CONFIGS = [("[[72, 12, 6]]", 0.004, 20, 1_000_000), ("[[144, 12, 12]]", 0.005, 20, 262_144), ("[[288, 12, 18]]", 0.006, 100, 16_384),
            ("[[90, 8, 10]]", 0.004, 20, 524_288), ("[[90, 8, 10]]", 0.005, 20, 524_288), ("[[90, 8, 10]]", 0.006, 20, 524_288),
            ("[[108, 8, 10]]", 0.004, 20, 524_288), ("[[108, 8, 10]]", 0.005, 20, 524_288), ("[[108, 8, 10]]", 0.006, 20, 524_288)]
+only = [a for a in sys.argv[1:] if not a.startswith('-')]
+if only:
+    CONFIGS = [c for c in CONFIGS if any(o in c[0] for o in only)]
 rows = []
 cache = {}
 for name, p, max_iter, shots in CONFIGS:
