@@ -678,11 +678,15 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     int want = ctas >= 4 ? 8 : (ctas >= 2 ? 16 : 32);
     if (const char *e = getenv("QLDPC_B200_EDGE_WARPS")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) want = w; }
     if (want != nwarps) {
-        nwarps = want;
-        L = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, nwarps);
-        if (!L.ok) return QB_OK;
-        smem = edge_smem_bytes(L, g.nw);
-        if (smem + 2048 > limit) return QB_OK;             // 2 KB: the kernel's static shared memory
+        // (a layout can fail with few warps -- more than 32 column slices per warp -- and still work with 32)
+        EdgeLayout L2 = build_edge_layout(g.m, g.n, dec->h_indptr.data(), dec->h_indices.data(), prior_h, want);
+        if (L2.ok && edge_smem_bytes(L2, g.nw) + 2048 <= limit) {
+            nwarps = want;
+            smem = edge_smem_bytes(L2, g.nw);
+            L = std::move(L2);
+        } else {
+            ctas = 1;
+        }
     }
     EdgePlan *p = new EdgePlan();
     p->threads = nwarps * 32; p->ctas_per_sm = ctas; p->smem = smem;

@@ -533,11 +533,17 @@ def test_edge_kernel_matches_compressed_state_kernel_and_oracle_on_random_graphs
         H3[r, 80 + (r - 30)] = 1                                                  # degree-1 rows -> +-inf posteriors
     H3[3, 85] = 1; H3[4, 85] = 1
     cases.append((H3, np.full(90, 3.0)))
+    # many low-degree rows and columns: more than two row slices per warp, several CTAs per SM, > 32 column slices for 8 warps
+    m4, n4 = 2400, 9000
+    H4 = np.zeros((m4, n4), np.int8)
+    for j in range(n4):
+        H4[rng.choice(m4, 2 + (j % 2), replace=False), j] = 1
+    cases.append((H4, np.full(n4, 2.0)))
     for ci, (H, prior) in enumerate(cases):
         Hc = csr_matrix(H); m, n = H.shape
         B = 64
-        e = (rng.random((B, n)) < 0.06).astype(np.int8)
-        syn = (e @ H.T % 2).astype(np.int8)
+        e = (rng.random((B, n)) < (0.06 if n < 1000 else 0.004)).astype(np.int8)
+        syn = (e.astype(np.int32) @ H.T.astype(np.int32) % 2).astype(np.int8)
         outs = []
         n_it = 140 if ci == 0 else 12          # > 128 iterations: the alpha schedule beyond the shared-memory copy
         for no_edge in ("", "1"):
