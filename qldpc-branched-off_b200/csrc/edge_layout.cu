@@ -138,7 +138,9 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     }
     {
         std::vector<int> cost(csl.size());
-        for (size_t i = 0; i < csl.size(); ++i) cost[i] = (csl[i].deg * 2 + 5) * (csl[i].cls == 15 ? 2 : 1);
+        for (size_t i = 0; i < csl.size(); ++i) cost[i] = (csl[i].deg * 8 + 8) * (csl[i].cls == 15 ? 2 : 1);
+        // (cutting the class-sorted list into contiguous equal-cost pieces -- long runs of one class per warp -- was measured
+        // 1.5 % slower than the LPT mix)
         auto sched = lpt(cost, nwarps);
         std::vector<CSlice> re;
         L.wc_ptr.assign(nwarps + 1, 0);
