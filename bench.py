@@ -65,9 +65,9 @@ def summarize_clocks(lines):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one minsum_edge_kernel launch, from the `ncu --set full` capture of
 # `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --shots-per-step 16384 --batch 16384`
-# (profiles/r1b_ncu_full_summary.txt): 4.3 MB + 508.8 MB for a 16384-shot launch = 31.3 KB per shot (the posteriors of the
+# (profiles/r1b_ncu_full_summary.txt): 3.3 MB + 507.8 MB for a 16384-shot launch = 31.2 KB per shot (the posteriors of the
 # non-converged sides, 0.946 x 8857 x 4 B, dominate: no re-reads), scaled to the launch size.
-NCU_TRAFFIC_BYTES_PER_SHOT = (4.26e6 + 508.84e6) / 16384
+NCU_TRAFFIC_BYTES_PER_SHOT = (3.26e6 + 507.83e6) / 16384
 
 
 def measured_peaks():
