@@ -515,7 +515,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
         const uint32_t target = s_target;
 
         bool conv = false;
-        int fin = a.max_iter - 1, wt = 0;
+        int fin = a.max_iter - 1;
         for (int it = 0; it < a.max_iter; ++it) {
             // ---- phase A --------------------------------------------------------------------------------
             const float alpha = it < 128 ? s_alpha[it] : a.alpha_d[it];
@@ -568,31 +568,61 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
                 if (s_wt == 0) { conv = true; fin = it; break; }                       // kernels.py:352-364
             }
         }
-        if (!conv && a.max_iter > 0 && a.fail_wt) {                                    // weight of the residual syndrome (OSD scheduling hint)
-            parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
-            __syncthreads();
-            if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
-            __syncthreads();
-            wt = s_wt;
-        }
-        // ---- output: hard decision back to natural column order ------------------------------------------
+        // ---- end of the shot: hard decision back to natural column order and, for a non-converged shot, the weight
+        // of its residual syndrome (OSD scheduling hint).  Both walk the variables whose hard decision is 1: their
+        // (slice, lane) pairs are listed once, then every (variable, edge) pair and every variable id gets a thread.
+        const bool need_wt = !conv && a.max_iter > 0 && a.fail_wt != nullptr;
         for (int w = tid; w < eg.nw; w += THREADS) hnat[w] = 0u;
-        if (tid == 0) s_target = 0u;
+        if (tid == 0) { s_target = 0u; s_pcount = 0; }
         __syncthreads();
         for (int t = tid; t < eg.n_csl; t += THREADS) {
             uint32_t bits = hperm[t];
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
-                const uint32_t vid = eg.var_id[t * 32 + b];
-                atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
+                const int slot = atomicAdd(&s_pcount, 1);
+                if (slot < PAR_LIST_CAP) s_plist[slot] = (uint16_t)(t * 32 + b);
             }
         }
         __syncthreads();
+        const int n_set = s_pcount;
+        if (n_set <= PAR_LIST_CAP) {
+            for (int i = tid; i < n_set * 8; i += THREADS) {
+                const int e = s_plist[i >> 3], t = e >> 5, b = e & 31, k0 = i & 7;
+                if (k0 == 7) {                                                           // one thread of the eight: the variable id
+                    const uint32_t vid = eg.var_id[e];
+                    atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
+                }
+                if (need_wt) {
+                    const uint32_t dx = cmeta[t];
+                    const int D = (dx >> 16) & 63, H = (D + 1) >> 1;
+                    const uint32_t *rp = eg.col_rowpos + (dx & 0xFFFFu) * 32;
+                    for (int k = k0; k < D; k += 8) {
+                        const uint32_t w = __ldg(&rp[edge_idx_off(H, k >> 1, b)]);
+                        const uint32_t pos = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+                        atomicXor(&par[pos >> 5], 1u << (pos & 31));
+                    }
+                }
+            }
+        } else {                                                                         // very heavy hard decision: per-slice walk
+            for (int t = tid; t < eg.n_csl; t += THREADS) {
+                uint32_t bits = hperm[t];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t vid = eg.var_id[t * 32 + b];
+                    atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
+                }
+            }
+            if (need_wt) parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
+        }
+        __syncthreads();
+        if (need_wt && warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
         for (int w = tid; w < eg.nw; w += THREADS) a.hard_bits[(size_t)shot * eg.nw + w] = hnat[w];
         const int done_shot = shot;
         shot = s_next;
         __syncthreads();
+        const int s_wt_done = need_wt ? s_wt : 0;                                       // (next written after two more barriers)
         // bookkeeping of the finished shot after the barrier: the round trip of the queue atomic overlaps the next
         // shot's syndrome load instead of holding all warps at the barrier
         if (tid == THREADS - 1) {
@@ -601,7 +631,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             if (!conv && a.fail_count) {
                 const int slot = atomicAdd(a.fail_count, 1);
                 a.fail_idx[slot] = done_shot;
-                if (a.fail_wt) a.fail_wt[slot] = wt;
+                if (a.fail_wt) a.fail_wt[slot] = s_wt_done;
             }
         }
     }
