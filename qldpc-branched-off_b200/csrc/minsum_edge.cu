@@ -18,7 +18,10 @@
 //            (XOR of per-column random signatures over the variables whose hard decision is 1 against the
 //            XOR of per-row masks over the syndrome) and confirmed exactly only when the fingerprints agree,
 //            so the common non-converged iteration never walks the graph a second time.
-// Iteration 0 reads Q = prior (unclipped, kernels.py:263-265) straight from a global image of E.
+// Iteration 0 reads Q = prior (unclipped, kernels.py:263-265) straight from a global image of E with LDG.128 (a TMA bulk
+// copy of the image into E between two shots, cp.async.bulk + mbarrier, was measured 3 % slower: E is only free for
+// ~3 k cycles and the per-SM bulk-copy rate does not cover 130 KB in that window, while the LDG path overlaps the
+// copy with the check-row arithmetic of iteration 0).
 // No fast-math: IEEE inf/NaN conventions are the reference's (degree-1 rows send +-inf).
 #include <math.h>
 #include <stdlib.h>
