@@ -708,7 +708,7 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     // several CTAs per SM for small codes: fewer warps each
     int ctas = (int)std::min<size_t>(4, (limit + 1024) / (smem + 2048 + 1024));
     if (const char *e = getenv("QLDPC_B200_EDGE_CTAS")) ctas = std::max(1, std::min(ctas, atoi(e)));
-    int want = ctas >= 4 ? 8 : (ctas >= 2 ? 16 : 32);
+    int want = ctas >= 3 ? 8 : (ctas >= 2 ? 16 : 32);     // 3-4 CTAs of 8 warps, 2 of 16, 1 of 32 per SM (64 registers per thread)
     if (const char *e = getenv("QLDPC_B200_EDGE_WARPS")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) want = w; }
     if (want != nwarps) {
         // (a layout can fail with few warps -- more than 32 column slices per warp -- and still work with 32)
