@@ -123,6 +123,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly one JSON line: NCCL's own log lines (NCCL_DEBUG=VERSION/INFO on some boxes) go to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
