@@ -10,7 +10,7 @@ __version__ = "0.1.0"
 
 _SRC_MODULES = ("codes", "codes.bb_code", "noise", "noise.builder", "noise.compiled", "noise.simulation",
                 "decoding", "decoding.sparse", "decoding.dense", "decoding.osd", "decoding.kernels",
-                "simulation", "simulation.engine", "utils", "utils.caching", "utils.plotting", "decoding.alpha")
+                "simulation", "simulation.engine", "utils", "utils.caching", "utils.plotting", "decoding.alpha", "decoding.scopt")
 
 
 def install_as_src():

@@ -143,8 +143,6 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
                    alpha_estimation_bins=50, precomputed_matrices=None, num_workers=None, base_seed=None,
                    use_jit=True, target_logical_errors=None, max_trials=None, scopt=False,
                    estimation_plot_dir=None, batch_size=None, **bb_params):
-    if scopt:
-        raise NotImplementedError("SCOPT beta estimation (reference scopt.py) is outside the GPU hot path")
     if base_seed is None:
         base_seed = np.random.randint(0, 2 ** 31)
     if alpha_mode not in (None, "dynamical", "alvarado", "alvarado-autoregressive"):
@@ -160,6 +158,20 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
         alpha_mode, use_dynamic_alpha, alvarado_alpha, matrices, llr_priors(matrices["channel_probsZ"]),
         llr_priors(matrices["channel_probsX"]), error_rate, maxIter, alpha_estimation_trials, alpha_estimation_bins,
         estimation_plot_dir)
+    if scopt:
+        # SCOPT beta pre-pass (engine.py:346-389; like the reference the estimate is reported, not yet used by the decoder)
+        from ..decoding.scopt import estimate_scopt_beta
+        fmt = lambda r: f"{r:.6g}".replace(".", "p")
+        betas = {}
+        for sd, key, ll in (("z", "HdecZ", llr_priors(matrices["channel_probsZ"])), ("x", "HdecX", llr_priors(matrices["channel_probsX"]))):
+            n_sd = np.asarray(matrices[key]).shape[1]
+            trials_sd = max(500, min(50000, int(2000 / (n_sd * error_rate))))
+            alpha_arg = alpha_z if sd == "z" else alpha_x
+            betas[sd] = estimate_scopt_beta(matrices[key], error_rate, trials=trials_sd, bins=alpha_estimation_bins, alpha=alpha_arg,
+                                            alpha_mode=alpha_mode, maxIter=maxIter, plot_dir=estimation_plot_dir,
+                                            plot_prefix=f"scopt_{fmt(error_rate)}_{sd}", llrs=ll)
+        _logger.info("SCOPT beta (estimated) for p=%.6g: beta_z=%.6g, beta_x=%.6g", error_rate, betas["z"][0], betas["x"][0])
+        extras.update(beta_z=betas["z"][0], beta_x=betas["x"][0], beta_r2_z=betas["z"][1], beta_r2_x=betas["x"][1])
     if max_trials is None:
         max_trials = num_trials if num_trials is not None else 1000000
     stop_on_errors = target_logical_errors is not None and target_logical_errors > 0

@@ -252,14 +252,36 @@ def alpha_fixture():
     np.savez_compressed(os.path.join(HERE, "alpha_72.npz"), **out)
 
 
+def scopt_fixture():
+    """SCOPT beta estimator (src/decoding/scopt.py) on the 72 code with seeded generators (pure-Python edge loop inside:
+    small trial counts)."""
+    from src.decoding.scopt import estimate_scopt_beta
+    name, p = "[[72, 12, 6]]", 0.004
+    d, bb = load_code(name)
+    M = load_matrices(os.path.join(REF, "matrix_cache"), compute_cache_key(d["Hx"], d["Hz"], d["Lx"], d["Lz"], int(d["distance"]), p))
+    out = {"p": p, "trials": 150, "maxIter": 12, "bins": 30}
+    for sd, H, cp in (("z", M["HdecZ"], M["channel_probsZ"]), ("x", M["HdecX"], M["channel_probsX"])):
+        ll = llrs(cp)
+        b, r2 = estimate_scopt_beta(H, p, trials=150, bins=30, alpha=1.0, alpha_mode="dynamical", maxIter=12,
+                                    rng=np.random.default_rng(11), llrs=ll)
+        out[f"dyn_{sd}"] = np.array([b, r2])
+        b2, r22 = estimate_scopt_beta(H, p, trials=100, bins=30, alpha=0.8, alpha_mode="alvarado", maxIter=8,
+                                      rng=np.random.default_rng(12), llrs=ll)
+        out[f"alv_{sd}"] = np.array([b2, r22])
+        print("scopt", sd, b, r2, b2, r22, flush=True)
+    np.savez_compressed(os.path.join(HERE, "scopt_72.npz"), **out)
+
+
 if __name__ == "__main__":
     # numba 0.65 cannot type np.clip on scalars inside bp_core (kernels.py:191), so the reference's
     # performBeliefPropagationFast does not compile here; run the same source un-jitted instead.
     import src.decoding.dense as _dense
     _dense.bp_core = rk.bp_core.py_func
-    which = sys.argv[1:] or ["builder", "small", "steane", "72", "144", "alpha"]
+    which = sys.argv[1:] or ["builder", "small", "steane", "72", "144", "alpha", "scopt"]
     if "alpha" in which:
         alpha_fixture()
+    if "scopt" in which:
+        scopt_fixture()
     if "builder" in which:
         builder_fixture()
     if "small" in which:

@@ -575,3 +575,31 @@ def test_edge_kernel_matches_compressed_state_kernel_and_oracle_on_random_graphs
             assert oc == c0[i] and of == f0[i]
             if oc:
                 assert np.array_equal(oh, h0[i])
+
+
+# ---- SCOPT beta pre-pass (reference scopt.py) on the GPU decoder -----------------------------------------------------
+def test_scopt_beta_vs_reference_golden_and_run_simulation():
+    """The batched float32 GPU decoder behind estimate_scopt_beta gives the reference's beta for the same seeded generator
+    up to the float32-vs-float64 perturbation of a histogram fit (golden: real reference, tests/golden/scopt_72.npz;
+    the exact float64 host logic is checked on the CPU in test_oracle_golden.py)."""
+    from qldpc_b200.decoding.scopt import estimate_scopt_beta
+    g = np.load(os.path.join(GOLDEN, "scopt_72.npz"))
+    p = float(g["p"])
+    M = matrices("72", p)
+    for sd in "zx":
+        H = csr_matrix(np.asarray(M["HdecZ" if sd == "z" else "HdecX"]) & 1)
+        prior = orc.llr_priors(M["channel_probsZ" if sd == "z" else "channel_probsX"])
+        b, r2 = estimate_scopt_beta(H, p, trials=int(g["trials"]), bins=int(g["bins"]), alpha=1.0, alpha_mode="dynamical",
+                                    maxIter=int(g["maxIter"]), rng=np.random.default_rng(11), llrs=prior)
+        assert abs(b - g[f"dyn_{sd}"][0]) < 5e-3 and abs(r2 - g[f"dyn_{sd}"][1]) < 5e-2, (sd, b, r2, g[f"dyn_{sd}"])
+        b, r2 = estimate_scopt_beta(H, p, trials=100, bins=30, alpha=0.8, alpha_mode="alvarado", maxIter=8,
+                                    rng=np.random.default_rng(12), llrs=prior)
+        assert abs(b - g[f"alv_{sd}"][0]) < 5e-3 and abs(r2 - g[f"alv_{sd}"][1]) < 5e-2, (sd, b, r2, g[f"alv_{sd}"])
+    # run_simulation(scopt=True) reports the reference's extra result fields (engine.py:482-486)
+    from qldpc_b200.simulation.engine import run_simulation
+    s = code_setup("72")
+    res = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], 0.004, num_trials=512, num_cycles=6, maxIter=10,
+                         alpha_mode="dynamical", base_seed=7, scopt=True, **s["bb"])
+    for k in ("beta_z", "beta_x", "beta_r2_z", "beta_r2_x", "logical_error_rate", "num_trials"):
+        assert k in res
+    assert res["num_trials"] == 512 and -1.0 < res["beta_z"] < 0.0 and -1.0 < res["beta_x"] < 0.0

@@ -179,3 +179,36 @@ def test_oracle_alpha_messages_reproduce_reference_alphas():
         t0.append(R[~bits]); t1.append(R[bits])
     a, r2 = _estimate_alpha_from_samples(np.concatenate(t0), np.concatenate(t1), bins=50)
     np.testing.assert_allclose([a, r2], g["alv_z"], rtol=1e-7, atol=1e-9)
+
+
+def test_scopt_beta_host_logic_vs_reference_golden():
+    """estimate_scopt_beta (reference scopt.py:8-176): sampling order, sample split, histogram and fit of the package's
+    implementation, with the float64 oracle standing in for the GPU decoder, reproduce the real reference's (beta, r2)
+    for the same seeded generators (tests/golden/scopt_72.npz, made by make_golden.py scopt)."""
+    import qldpc_b200  # noqa: F401
+    from qldpc_b200.decoding.scopt import estimate_scopt_beta
+    from scipy.sparse import csr_matrix
+    g = np.load(os.path.join(GOLDEN, "scopt_72.npz"))
+    p = float(g["p"])
+    M = matrices("72", p)
+    for sd in "zx":
+        H = csr_matrix(np.asarray(M["HdecZ" if sd == "z" else "HdecX"]) & 1)
+        prior = orc.llr_priors(M["channel_probsZ" if sd == "z" else "channel_probsX"])
+
+        def decoder(max_iter, **kw):
+            def decode(syn):
+                return np.stack([orc.performMinSum_Symmetric_Sparse(H, s_, prior, maxIter=max_iter, **kw)[2] for s_ in syn])
+            return decode
+        b, r2 = estimate_scopt_beta(H, p, trials=int(g["trials"]), bins=int(g["bins"]), alpha=1.0, alpha_mode="dynamical",
+                                    maxIter=int(g["maxIter"]), rng=np.random.default_rng(11), llrs=prior,
+                                    _decode=decoder(int(g["maxIter"]), alpha=1.0, alpha_mode="dynamical"))
+        np.testing.assert_allclose([b, r2], g[f"dyn_{sd}"], rtol=1e-6)
+        b, r2 = estimate_scopt_beta(H, p, trials=100, bins=30, alpha=0.8, alpha_mode="alvarado", maxIter=8,
+                                    rng=np.random.default_rng(12), llrs=prior, _decode=decoder(8, alpha=0.8, alpha_mode="alvarado"))
+        np.testing.assert_allclose([b, r2], g[f"alv_{sd}"], rtol=1e-6)
+    with pytest.raises(ValueError):
+        estimate_scopt_beta(H, 0.7, llrs=prior)
+    with pytest.raises(ValueError):
+        estimate_scopt_beta(H, p, alpha_mode="nope", llrs=prior)
+    with pytest.raises(ValueError):
+        estimate_scopt_beta(H, p, maxIter=0, llrs=prior)
