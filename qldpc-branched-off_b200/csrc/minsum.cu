@@ -180,7 +180,7 @@ __device__ __forceinline__ void col_chunk(const uint4 *chk, int crow, uint4 e4, 
 }
 
 template <int S>
-__global__ void __launch_bounds__(MS_THREADS, (S <= 2 ? 2 : 1))
+__global__ void __launch_bounds__((S == 1 ? 1024 : MS_THREADS), (S == 2 ? 2 : 1))
 minsum_fast_kernel(GraphDev g, MinsumLaunch a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -669,7 +669,8 @@ static int launch_fast(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
     // thread count: 512 while at most two CTAs fit an SM, fewer for small codes so that several CTAs share it
     int threads = MS_THREADS;
     if (ctas_per_sm > 2) threads = 256;
-    if (const char *e = getenv("QLDPC_B200_MS_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= MS_THREADS && t % 32 == 0) threads = t; }
+    if (S == 1 && ctas_per_sm == 1) threads = 1024;       // one large shot per SM (e.g. [[288,12,18]]): all 32 warps on it
+    if (const char *e = getenv("QLDPC_B200_MS_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= (S == 1 ? 1024 : MS_THREADS) && t % 32 == 0) threads = t; }
     ctas_per_sm = std::min(ctas_per_sm, 2048 / threads);
     const int grid = std::max(1, std::min(tiles, dec->sm_count * ctas_per_sm));
     minsum_fast_kernel<S><<<grid, threads, smem, st>>>(dec->g, a);
