@@ -254,7 +254,7 @@ void qb_decoder_destroy(qb_decoder *dec)
     for (void *p : dec->owned) cudaFree(p);
     edge_plan_destroy(dec->edge);
     if (dec->d_alpha) cudaFree(dec->d_alpha);
-    dec->scratch.release(); dec->work.release();
+    dec->scratch.release(); dec->work.release(); dec->ovf.release();
     delete dec;
 }
 

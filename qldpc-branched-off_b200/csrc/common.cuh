@@ -83,6 +83,7 @@ struct qb_decoder {
     int alpha_cap = 0;
     qb::Scratch scratch;        // host-API staging
     qb::Scratch work;           // kernel workspaces (general min-sum messages, OSD spill)
+    qb::Scratch ovf;            // OSD: sides the one-warp kernel hands to the four-warp kernel (count + list)
     int sm_count = 148;
     int max_smem_optin = 0;
     qb::EdgePlan *edge = nullptr;   // nullptr: graph does not fit the per-edge kernel
@@ -140,6 +141,7 @@ struct OsdLaunch {
     int exact_rows;             // emulate the reference's pivot-row order (inconsistent syndromes)
 };
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
+int launch_osd0_warp(qb_decoder *dec, const OsdLaunch &a, int32_t *overflow_count_d, int32_t *overflow_idx_d, int *used, cudaStream_t st);
 // order the failure queue by descending residual weight (longest elimination first)
 int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail_d, int32_t *sorted_idx, cudaStream_t st);
 

@@ -393,6 +393,29 @@ def test_pipeline_full_size_properties_gross():
     dec.close()
 
 
+def test_osd_one_warp_kernel_matches_default_kernel():
+    """The opt-in one-warp-per-side OSD-0 kernel (osd_warp.cu, QLDPC_B200_OSD_WARP=1) gives the flags of the default
+    four-warp kernel on the gross and the 72-qubit code (shared-memory-resident and spilled stored columns)."""
+    from qldpc_b200.simulation.engine import ShotEngine
+    for tag, p, shots in (("144", 0.005, 3000), ("72", 0.006, 4000)):
+        s = code_setup(tag); M = matrices(tag, p)
+        cfg = _lib.make_config(20, _lib.QB_ALPHA_DYNAMIC)
+        outs = []
+        for env in ({}, {"QLDPC_B200_OSD_WARP": "1", "QLDPC_B200_OSD_WARP_SIDES": "8"},
+                    {"QLDPC_B200_OSD_WARP": "1", "QLDPC_B200_OSD_WARP_SIDES": "24"}):
+            os.environ.update(env)
+            try:
+                eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=2048)
+                outs.append(eng.pipeline.run(7, 0, shots, p, cfg, want_flags=True))
+                eng.close()
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        assert outs[0][0][4] > 0
+        for c, f in outs[1:]:
+            assert np.array_equal(c, outs[0][0]) and np.array_equal(f, outs[0][1])
+
+
 def test_run_simulation_api_and_early_stop():
     from qldpc_b200.simulation.engine import run_simulation
     s = code_setup("72"); p = 0.006
