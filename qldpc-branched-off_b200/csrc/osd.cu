@@ -30,15 +30,17 @@ namespace qb {
 
 constexpr int OSD_CTAS_PER_SM = 9;
 constexpr int OSD_NW = OSD_THREADS / 32;   // warps per CTA = candidates reduced per round
-constexpr int SEL_BINS = 2048;             // histogram bins: float bits 30..20 (8 bins per octave)
-constexpr int SEL_SHIFT = 20;
+constexpr int SEL_BINS = 2048;             // histogram bins: 64 per octave over 2^-25 .. 2^7, clamped (monotone in the key)
+constexpr int SEL_SHIFT = 17;
+constexpr int SEL_BASE = (127 - 25) << 6;
 constexpr int SEL_CAP = 1024;              // candidates materialised per selection window
-constexpr int SEL_MIN = 384;               // a window is closed once it holds at least this many
+constexpr int SEL_MIN = 640;               // a window is closed once it holds at least this many
 
 struct OsdArgs {
     GraphDev g;
     OsdLaunch a;
     int tcap;             // T columns resident in shared memory; the rest spills to gT
+    int sel_min;          // a selection window is closed once it holds at least this many candidates
     int cstride;          // words per T column (mw + 1 when mw is even: conflict-free column-parallel reads)
     int rank_cap;         // min(m, n)
     uint32_t *gT;         // [grid][(rank_cap - tcap) * cstride] spill
@@ -53,6 +55,7 @@ struct OsdArgs {
     uint16_t *g_pivpos;   // [grid][rank_cap] pivot positions in the ordering (only filled when pivots_out is set)
 };
 
+__device__ __forceinline__ int sel_bin(uint32_t key) { return min(max((int)(key >> SEL_SHIFT) - SEL_BASE, 0), SEL_BINS - 1); }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t r; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r)); return r; }
 
 // Stable LSD radix sort (4 x 8 bit) of idx[] by keys[idx]; warps own contiguous segments so the
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
             for (int j0 = tid; j0 < n; j0 += 8 * OSD_THREADS) {      // 8 independent loads in flight per thread
                 uint32_t kb[8];
 #pragma unroll
-                for (int u8 = 0; u8 < 8; ++u8) { const int j = j0 + u8 * OSD_THREADS; kb[u8] = j < n ? (__float_as_uint(fabsf(post[j])) >> SEL_SHIFT) : 0xFFFFFFFFu; }
+                for (int u8 = 0; u8 < 8; ++u8) { const int j = j0 + u8 * OSD_THREADS; kb[u8] = j < n ? (uint32_t)sel_bin(__float_as_uint(fabsf(post[j]))) : 0xFFFFFFFFu; }
 #pragma unroll
                 for (int u8 = 0; u8 < 8; ++u8) if (kb[u8] != 0xFFFFFFFFu) atomicAdd(&s_hist[kb[u8]], 1u);
             }
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                     for (int b = tid; b < SEL_BINS; b += blockDim.x) hist[b] = 0u;
                     __syncthreads();
                     for (int j = tid; j < n; j += blockDim.x) {
-                        const int b = __float_as_uint(fabsf(post[j])) >> SEL_SHIFT;
+                        const int b = sel_bin(__float_as_uint(fabsf(post[j])));
                         if (b >= bin_next) atomicAdd(&hist[b], 1u);
                     }
                     __syncthreads();
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
                         if (b < SEL_BINS) hist[b] = ((uint32_t)min(cum + inc - cnt, 65535) << 16) | (uint32_t)cnt;
                         const uint32_t over = __ballot_sync(0xFFFFFFFFu, cum + inc > SEL_CAP);
-                        const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum + inc >= SEL_MIN);
+                        const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum + inc >= P.sel_min);
                         int last = 31;
                         if (over | enough) {
                             const int fo = over ? __ffs(over) - 1 : 32, fe = enough ? __ffs(enough) - 1 : 32;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
 #pragma unroll
                         for (int u8 = 0; u8 < 8; ++u8) {
                             const uint32_t key = kb[u8];
-                            const int b = key >> SEL_SHIFT;
+                            const int b = sel_bin(key);
                             if (key != 0xFFFFFFFFu && b >= bin_next && b <= bin_hi) {
                                 const uint32_t old = atomicSub(&hist[b], 1u);       // count down: consumed bins end at count 0
                                 const int slot = (int)(old >> 16) + (int)(old & 0xFFFFu) - 1;
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                     for (int i = tid; i < M; i += blockDim.x) {
                         const uint32_t key = listK[i];
                         const uint16_t id = listI[i];
-                        const int b = key >> SEL_SHIFT;
+                        const int b = sel_bin(key);
                         const int lo = (int)(hist[b] >> 16);
                         int hi2 = M;
                         if (b < bin_hi) hi2 = (int)(hist[b + 1] >> 16);       // offsets are non-decreasing over the window
@@ -481,6 +484,8 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.g = g; P.a = a;
     P.rank_cap = std::min(g.m, g.n);
     P.cstride = (g.mw & 1) ? g.mw : g.mw + 1;
+    P.sel_min = SEL_MIN;
+    if (const char *e = getenv("QLDPC_B200_OSD_SEL_MIN")) { const int v = atoi(e); if (v >= 32 && v <= SEL_CAP) P.sel_min = v; }
     const int n_pad2 = (g.n + 1) & ~1;
     const size_t fixed = sizeof(uint16_t) * (EXACTROWS ? 5 : 3) * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
     const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
