@@ -53,6 +53,7 @@ struct OsdArgs {
     uint32_t *g_cnt;      // [grid][256 * OSD_NW]
     int32_t *work_counter; // device counter, zero at launch
     uint16_t *g_pivpos;   // [grid][rank_cap] pivot positions in the ordering (only filled when pivots_out is set)
+    uint32_t *g_piv;      // [grid][rank_cap] pivot row | column << 16 (written once per pivot, read once at the end)
 };
 
 __device__ __forceinline__ int sel_bin(uint32_t key) { return min(max((int)(key >> SEL_SHIFT) - SEL_BASE, 0), SEL_BINS - 1); }
@@ -136,8 +137,6 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         row_at_pos = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
     }
     int16_t *pivcol_of_row = reinterpret_cast<int16_t *>(sp); sp += sizeof(int16_t) * g.m_pad;
-    uint16_t *piv_row = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;
-    uint16_t *piv_col = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * g.m_pad;   // column index
     uint32_t *npmask = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
     uint32_t *sv = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
     uint32_t *pv = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * 32 * WPL;
@@ -150,6 +149,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
     uint32_t *Tsm = regionX;
     uint32_t *Tgl = P.gT ? P.gT + (size_t)blockIdx.x * (size_t)(P.rank_cap - P.tcap) * cs : nullptr;
     uint16_t *piv_pos = P.g_pivpos + (size_t)blockIdx.x * P.rank_cap;
+    uint32_t *piv_rc = P.g_piv + (size_t)blockIdx.x * P.rank_cap;
     __shared__ int s_flags[NW];
     __shared__ int s_rho, s_binhi, s_wincount;
 
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                             pos_of_row[rt] = (uint16_t)q; pos_of_row[rho] = (uint16_t)t;
                         }
                         pivcol_of_row[rho] = (int16_t)t;
-                        piv_row[t] = (uint16_t)rho; piv_col[t] = (uint16_t)myj;
+                        piv_rc[t] = (uint32_t)rho | ((uint32_t)myj << 16);
                         if (P.a.pivots_out) piv_pos[t] = (uint16_t)c;
                         s_rho = rho;
                     }
@@ -462,9 +462,10 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         __syncthreads();
         uint32_t *hard_rw = P.a.hard_bits + (size_t)shot * g.nw;
         for (int i = tid; i < t; i += blockDim.x) {
-            const int rho = piv_row[i];
+            const uint32_t prc = piv_rc[i];
+            const int rho = prc & 0xFFFFu;
             if ((sv[rho >> 5] >> (rho & 31)) & 1u) {
-                const int j = (int)piv_col[i];
+                const int j = (int)(prc >> 16);
                 atomicXor(&hard_rw[j >> 5], 1u << (j & 31));
             }
         }
@@ -487,7 +488,7 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.sel_min = SEL_MIN;
     if (const char *e = getenv("QLDPC_B200_OSD_SEL_MIN")) { const int v = atoi(e); if (v >= 32 && v <= SEL_CAP) P.sel_min = v; }
     const int n_pad2 = (g.n + 1) & ~1;
-    const size_t fixed = sizeof(uint16_t) * (EXACTROWS ? 5 : 3) * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
+    const size_t fixed = sizeof(uint16_t) * (EXACTROWS ? 3 : 1) * (size_t)g.m_pad + sizeof(uint32_t) * 32 * WPL * 3 + sizeof(uint16_t) * SEL_CAP;
     const size_t sel_b = sizeof(uint32_t) * SEL_BINS + sizeof(uint32_t) * SEL_CAP + sizeof(uint16_t) * SEL_CAP + 16;
     const size_t budget = (size_t)dec->max_smem_optin - 1024;
     const size_t colb = sizeof(uint32_t) * (size_t)P.cstride;
@@ -511,7 +512,8 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t G = (size_t)grid;
     const size_t b_pp = sizeof(uint16_t) * (size_t)std::max(1, P.rank_cap);
-    const size_t need = 256 + al(G * b_pp) + al(G * spill) + al(G * b_hist) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
+    const size_t b_pr = sizeof(uint32_t) * (size_t)std::max(1, P.rank_cap);
+    const size_t need = 256 + al(G * b_pp) + al(G * b_pr) + al(G * spill) + al(G * b_hist) + al(G * b_lk) + al(G * b_li) + al(G * b_keys) + al(G * b_idx) + al(G * b_cnt) + 256;
     if (int rc = dec->work.ensure(need)) return rc;
     unsigned char *p = dec->work.as<unsigned char>();
     P.work_counter = reinterpret_cast<int32_t *>(p); p += 256;
@@ -523,7 +525,8 @@ static int launch_osd_wpl(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     P.g_keys = reinterpret_cast<uint32_t *>(p); p += al(G * b_keys);
     P.g_idx = reinterpret_cast<uint16_t *>(p); p += al(G * b_idx);
     P.g_cnt = reinterpret_cast<uint32_t *>(p); p += al(G * b_cnt);
-    P.g_pivpos = reinterpret_cast<uint16_t *>(p);
+    P.g_pivpos = reinterpret_cast<uint16_t *>(p); p += al(G * b_pp);
+    P.g_piv = reinterpret_cast<uint32_t *>(p);
     QB_CUDA(cudaFuncSetAttribute(osd0_kernel<WPL, EXACTROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     osd0_kernel<WPL, EXACTROWS><<<grid, OSD_THREADS, smem, st>>>(P);
     QB_CUDA(cudaGetLastError());
