@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                             best = min(best, (uint32_t)(w * 32 + __ffs(bits) - 1));
                         }
                     }
-                    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                    best = __reduce_min_sync(0xFFFFFFFFu, best);
                     const int q = EXACTROWS ? (int)(best >> 16) : 0, rho = best & 0xFFFF;
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) {
@@ -433,16 +433,17 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
 #pragma unroll
                     for (int i = 0; i < WPL; ++i) if (i == ri && lane == rl) npr[i] &= ~rbit;
                 }
-                // (c) stored columns of earlier pivots; column x is only ever updated by warp (x/32) % NW, so
-                // successive pivots need no barrier between their updates.  32 columns are tested per read.
-                for (int x0 = warp * 32; x0 < t; x0 += NW * 32) {
-                    const int x = x0 + lane;
+                // (c) stored columns of earlier pivots; column x is only ever updated by warp x % NW, so successive
+                // pivots need no barrier between their updates, and the work is spread over the warps for any t.
+                // 32 columns are tested per read.
+                for (int i0 = 0; i0 * NW + warp < t; i0 += 32) {
+                    const int x = (i0 + lane) * NW + warp;
                     const bool has = x < t && (ldT(x, rw) & rbit) != 0u;
                     uint32_t msk = __ballot_sync(0xFFFFFFFFu, has);
                     while (msk) {
                         const int b = __ffs(msk) - 1; msk &= msk - 1;
 #pragma unroll
-                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) xorT(x0 + b, w, u[i]); }
+                        for (int i = 0; i < WPL; ++i) { const int w = lane + 32 * i; if (w < mw) xorT((i0 + b) * NW + warp, w, u[i]); }
                     }
                 }
                 ++t;
