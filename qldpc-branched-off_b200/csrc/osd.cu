@@ -567,8 +567,9 @@ int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     }
     if (!a.ordering && !a.post) { set_error("OSD-0 needs posteriors or an ordering"); return QB_ERR_ARG; }
     const int wpl = ceil_div(g.mw, 32);
-    if (!a.exact_rows && a.n_fail_d && a.fail_idx) {
-        // pipeline path: one warp per side (osd_warp.cu); the four-warp kernel below only takes what it hands back
+    const char *warp_opt = getenv("QLDPC_B200_OSD_WARP");
+    if (warp_opt && warp_opt[0] == '1' && !a.exact_rows && a.n_fail_d && a.fail_idx) {
+        // opt-in experiment: one warp per side (osd_warp.cu); the four-warp kernel below only takes what it hands back
         if (int rc = dec->ovf.ensure(((size_t)a.F + 64) * sizeof(int32_t))) return rc;
         int32_t *cnt = dec->ovf.as<int32_t>(), *idx = cnt + 64;
         int used = 0;
