@@ -116,6 +116,13 @@ __device__ void full_radix_sort(const uint32_t *keys, uint16_t *idx0, uint16_t *
     }
 }
 
+#ifdef QB_OSD_PROFILE
+// instrumented build (tools/osd_side_profile.py): per side {pivots, candidates examined, cycles, start time}
+constexpr int OSD_PROF_CAP = 1 << 18;
+__device__ unsigned long long g_osd_prof[OSD_PROF_CAP * 8];   // + cycles of: setup/residual, histogram, windows, writeback
+__device__ int g_osd_prof_n;
+#endif
+
 // EXACTROWS: choose each pivot row exactly like the reference's swapped row order (needed only when the
 // syndrome may be inconsistent, i.e. outside the column space of H, where the result depends on it);
 // for consistent syndromes -- every simulated shot -- the solution is unique and the lowest free row is used.
@@ -164,6 +171,10 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         __syncthreads();
         if (qi >= F) break;
         const int shot = P.a.fail_idx ? P.a.fail_idx[qi] : qi;
+#ifdef QB_OSD_PROFILE
+        const long long prof_t0 = clock64();
+        long long prof_win = 0, prof_t1 = 0, prof_t2 = 0, prof_t3 = 0;
+#endif
         const uint32_t *hard = P.a.hard_bits + (size_t)shot * g.nw;
         const int32_t *ext_order = P.a.ordering ? P.a.ordering + (size_t)shot * n : nullptr;
         const float *post = P.a.post ? P.a.post + (size_t)shot * n : nullptr;
@@ -188,6 +199,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                     for (int p = g.colptr[j]; p < g.colptr[j + 1]; ++p) { const int r = g.rowidx[p]; atomicXor(&sv[r >> 5], 1u << (r & 31)); }
             }
         }
+#ifdef QB_OSD_PROFILE
+        prof_t1 = clock64();
+#endif
         // ---- 2a. histogram of |posterior| bit patterns (selection pass 1) ---------------------------
         if (!ext_order) {
             for (int j0 = tid; j0 < n; j0 += 8 * OSD_THREADS) {      // 8 independent loads in flight per thread
@@ -200,6 +214,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         }
         __syncthreads();
 
+#ifdef QB_OSD_PROFILE
+        prof_t2 = clock64();
+#endif
         // ordering modes: 0 = caller-supplied, 1 = selection windows, 2 = full sort in global scratch
         int mode = ext_order ? 0 : 1;
         int bin_next = 0;                 // first histogram bin not yet consumed
@@ -256,6 +273,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         int c0 = 0;
         while (!done && c0 < n && t < P.rank_cap) {
             // ---- 2b. materialise the next window of candidates, sorted by (|posterior|, index) --------
+#ifdef QB_OSD_PROFILE
+            const long long prof_w0 = clock64();
+#endif
             if (c0 >= win_end && mode == 1) {
                 if (t > 0) {       // T now lives in regionX: later windows use the global scratch
                     hist = P.g_hist + (size_t)blockIdx.x * SEL_BINS;
@@ -342,6 +362,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
                 __syncthreads();
             }
 
+#ifdef QB_OSD_PROFILE
+            prof_win += clock64() - prof_w0;
+#endif
             // ---- 3. reduce NW candidates against the current T -----------------------------------------
             const int c = c0 + warp;
             const bool have = c < win_end && c < n;
@@ -455,6 +478,9 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
             if (mode == 1 && c0 > win_end) c0 = win_end;   // do not skip candidates of the next window
         }
 
+#ifdef QB_OSD_PROFILE
+        prof_t3 = clock64();
+#endif
         // ---- 5. solution = hard ^ e, e[ordering[pivot_col]] = s_reduced[pivot_row] ---------------
         if (warp == 0) {
 #pragma unroll
@@ -474,6 +500,18 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
             for (int i = tid; i < P.rank_cap; i += blockDim.x)
                 P.a.pivots_out[(size_t)shot * P.rank_cap + i] = i < t ? (int)piv_pos[i] : -1;
         if (P.a.rank_out && tid == 0) P.a.rank_out[shot] = t;
+#ifdef QB_OSD_PROFILE
+        if (tid == 0) {
+            const int slot = atomicAdd(&g_osd_prof_n, 1);
+            if (slot < OSD_PROF_CAP) {
+                g_osd_prof[slot * 8 + 0] = (unsigned long long)t; g_osd_prof[slot * 8 + 1] = (unsigned long long)c0;
+                g_osd_prof[slot * 8 + 2] = (unsigned long long)(clock64() - prof_t0);
+                g_osd_prof[slot * 8 + 4] = (unsigned long long)(prof_t1 - prof_t0); g_osd_prof[slot * 8 + 5] = (unsigned long long)(prof_t2 - prof_t1);
+                g_osd_prof[slot * 8 + 6] = (unsigned long long)prof_win; g_osd_prof[slot * 8 + 7] = (unsigned long long)(clock64() - prof_t3);
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_osd_prof[slot * 8 + 3] = gt;
+            }
+        }
+#endif
         __syncthreads();
     }
 }
@@ -656,3 +694,18 @@ int launch_gf2_dense(uint32_t *A, uint32_t *b, int m, int n, int nw, int32_t *pr
 }
 
 }  // namespace qb
+
+#ifdef QB_OSD_PROFILE
+// copies the per-side records to the host and resets the counter; returns the number of records
+extern "C" int qb_debug_osd_profile(unsigned long long *out_h, int max_records)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, qb::g_osd_prof_n, sizeof(int));
+    n = std::min(std::min(n, qb::OSD_PROF_CAP), max_records);
+    if (n > 0) cudaMemcpyFromSymbol(out_h, qb::g_osd_prof, sizeof(unsigned long long) * 8 * (size_t)n);
+    const int zero = 0;
+    cudaMemcpyToSymbol(qb::g_osd_prof_n, &zero, sizeof(int));
+    return n;
+}
+#endif
