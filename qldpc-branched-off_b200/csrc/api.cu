@@ -629,6 +629,8 @@ struct qb_pipeline {
     int max_batch = 0;
     cudaStream_t st = nullptr;        // stream all pipeline work is issued on
     cudaStream_t own_st = nullptr;    // the pipeline's own stream (default)
+    cudaStream_t side_st = nullptr;   // second stream: the X side's OSD-0 runs beside the Z side's and fills its tail
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t *synZ = nullptr, *synX = nullptr, *trueZ = nullptr, *trueX = nullptr, *hardZ = nullptr, *hardX = nullptr;
     uint8_t *convZ = nullptr, *convX = nullptr, *flags = nullptr;
     int32_t *itZ = nullptr, *itX = nullptr, *failZ = nullptr, *failX = nullptr, *nfail = nullptr;   // nfail[2]
@@ -694,18 +696,24 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
     }
     if (timed) QB_CUDA(cudaEventRecord(ev[EV_MINSUM], st));
     if (cfg->use_osd) {
+        // The two sides are independent (own decoders, own workspaces): the X side is issued on a second stream, so
+        // that its CTAs take the SMs the Z launch frees while its last, longest eliminations finish.
+        const bool fork = p->dz != p->dx && p->side_st != nullptr;
+        if (fork) { QB_CUDA(cudaEventRecord(p->ev_fork, st)); QB_CUDA(cudaStreamWaitEvent(p->side_st, p->ev_fork, 0)); }
         for (int side = 0; side < 2; ++side) {
             qb_decoder *d = side ? p->dx : p->dz;
+            cudaStream_t ss = (fork && side) ? p->side_st : st;
             if (int rc = launch_sort_failures(side ? p->failX : p->failZ, side ? p->fwX : p->fwZ, p->nfail + side,
-                                              side ? p->sortX : p->sortZ, st)) return rc;
+                                              side ? p->sortX : p->sortZ, ss)) return rc;
             p->stats.kernel_launches++;
             OsdLaunch a{};
             a.syn_bits = side ? p->synX : p->synZ; a.hard_bits = side ? p->hardX : p->hardZ;
             a.post = side ? p->postX : p->postZ; a.fail_idx = side ? p->sortX : p->sortZ;
             a.F = B; a.n_fail_d = p->nfail + side;
-            if (int rc = launch_osd0(d, a, st)) return rc;
+            if (int rc = launch_osd0(d, a, ss)) return rc;
             p->stats.kernel_launches++;
         }
+        if (fork) { QB_CUDA(cudaEventRecord(p->ev_join, p->side_st)); QB_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0)); }
     }
     if (timed) QB_CUDA(cudaEventRecord(ev[EV_OSD], st));
     if (int rc = launch_logical_check(p->dz, p->hardZ, p->trueZ, B, p->flags, 0, p->counts, 0, st)) return rc;
@@ -760,6 +768,9 @@ int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_
     const GraphDev &gz = decZ->g, &gx = decX->g;
     int rc = QB_OK;
     if (cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking) != cudaSuccess) rc = QB_ERR_CUDA;
+    if (!rc && (cudaStreamCreateWithFlags(&p->side_st, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)) rc = QB_ERR_CUDA;
     p->st = p->own_st;
 #define AL(ptr, cnt) if (!rc) rc = dalloc(p, &p->ptr, cnt);
     AL(synZ, B * gz.mw) AL(synX, B * gx.mw) AL(trueZ, B) AL(trueX, B) AL(hardZ, B * gz.nw) AL(hardX, B * gx.nw)
@@ -783,6 +794,9 @@ void qb_pipeline_destroy(qb_pipeline *p)
     for (void *q : p->owned) cudaFree(q);
     if (p->events) cudaFree(p->events);
     for (auto e : p->evs) if (e) cudaEventDestroy(e);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->side_st) cudaStreamDestroy(p->side_st);
     if (p->own_st) cudaStreamDestroy(p->own_st);
     delete p;
 }
