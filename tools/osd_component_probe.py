@@ -7,7 +7,6 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import helpers
 import qldpc_b200
 from qldpc_b200 import _lib
-from oracle import oracle as orc
 import scipy.sparse as sp
 from scipy.sparse.csgraph import connected_components
 
@@ -19,7 +18,9 @@ B = 64
 szb, _, sxb, _, _ = smp.sample(4321, 0, B, p)
 H = np.asarray(M["HdecX"]) & 1
 Hc = sp.csr_matrix(H); Hcsc = sp.csc_matrix(H)
-prior = orc.llr_priors(M["channel_probsX"])
+probs = np.asarray(M["channel_probsX"], dtype=np.float64)
+with np.errstate(all="ignore"):
+    prior = np.clip(np.nan_to_num(np.log((1 - probs) / probs)), -50, 50)      # engine.py:210-212
 dec = _lib.Decoder(Hc.indptr, Hc.indices, H.shape[1], prior)
 m, n = H.shape
 syn = helpers.unpack(sxb.view(np.uint8), m).astype(np.int8)
