@@ -25,6 +25,8 @@
 // warp of the SM sits in a different part of the 3.8k-instruction program); hiding that needs ~40 warps per SM, and
 // the 18-20 KB of stored columns per side allow 10 (or 16-24 with most columns spilled to global memory, which
 // then shows up as long-scoreboard stalls).  profiles/r1b_microbenchmarks.txt has the numbers.
+// Way out: an elimination touches only ~1.1 rows per pivot (141 of 1008 on average), so with rows renumbered on
+// first touch the stored columns of a side take ~2-8 KB instead of 18-20 KB and 40+ sides fit an SM.
 #include <algorithm>
 
 #include "common.cuh"
