@@ -135,6 +135,15 @@ int qb_osd0_batch(qb_decoder *dec, const uint32_t *syn_bits_d, uint32_t *hard_bi
 int qb_osd0_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h, const double *llr_h,
                  const int32_t *ordering_h, int32_t B, int64_t *solution_h, int32_t *rank_h, int32_t *pivots_h);
 
+/* The pipeline's own OSD-0 path (the kernels qb_pipeline_run* launch for the non-converged sides of a batch; pivot rows
+ * are free to differ from the reference's because simulated syndromes are always consistent) on
+ * host-supplied float32 posteriors -- the entry the parity tests use to drive that path with crafted reliabilities
+ * (mass ties, more candidates than one selection window).  syndrome_h int8 [B][m] must lie in the column space of H;
+ * hard_h int8 [B][n]; post_h float32 [B][n]; solution_h int8 [B][n] = hard ^ e (osd.py:19-25);
+ * osd_info_h (nullable) [B] = pivots_used | path << 16 as in qb_pipeline_last_batch_detail. */
+int qb_osd0_pipeline_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h, const float *post_h, int32_t B,
+                          int8_t *solution_h, int32_t *osd_info_h);
+
 /* Dense GF(2) Gauss-Jordan of an arbitrary m x n 0/1 matrix with right-hand side:
  * gf2_elimination (src/decoding/kernels.py:6-34) and gf2_elimination_packed (:98-106).
  * A_h int64 [m][n] and b_h int64 [m] are reduced in place (the reference mutates them);
@@ -205,6 +214,18 @@ int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const u
 int qb_pipeline_decode_host(qb_pipeline *p, const int8_t *sparseZ_h, const uint32_t *trueZ_h,
                             const int8_t *sparseX_h, const uint32_t *trueX_h, int32_t B,
                             const qb_decode_config *cfg, int64_t *counts_h, uint8_t *flags_h);
+
+/* Per-shot detail of the LAST batch a qb_pipeline_run* call decoded (parity testing of the pipeline's own OSD-0
+ * kernels against the reference's elimination, src/decoding/osd.py:5-29 + kernels.py:49-96, on the very posteriors
+ * the pipeline's min-sum produced).  side 0 = Z, 1 = X.  All outputs nullable:
+ *   hard_bits_h [B][ceil(n/32)]  final corrections (after OSD-0 on the non-converged sides, engine.py:96-97);
+ *   post_h      [B][n]           float32 min-sum posteriors; rows of converged sides are stale / unspecified
+ *                                (the pipeline writes posteriors only for sides that go to OSD); the hard decision
+ *                                min-sum handed to OSD is post < 0 (kernels.py:349);
+ *   osd_info_h  [B]              0 for converged sides, else pivots_used | path << 16 with path 1 = free-row kernel,
+ *                                2 = full-width kernel (recorded only after qb_pipeline_enable_detail(p, 1)). */
+int qb_pipeline_enable_detail(qb_pipeline *p, int on);
+int qb_pipeline_last_batch_detail(qb_pipeline *p, int32_t side, uint32_t *hard_bits_h, float *post_h, int32_t *osd_info_h);
 
 /* timing / accounting of the last qb_pipeline_run* call (device time from CUDA events, ms) */
 typedef struct {

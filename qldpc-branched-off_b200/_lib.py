@@ -43,7 +43,8 @@ EXPORTS = [
     "qb_syndrome_check_host", "qb_osd0_batch", "qb_osd0_host", "qb_gf2_eliminate_host", "qb_sampler_create",
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
-    "qb_pipeline_decode_host", "qb_pipeline_last_stats",
+    "qb_pipeline_decode_host", "qb_pipeline_last_stats", "qb_pipeline_enable_detail", "qb_pipeline_last_batch_detail",
+    "qb_osd0_pipeline_host",
 ]
 
 
@@ -197,6 +198,17 @@ class Decoder:
         check(load().qb_osd0_host(self._h, ptr(syn), ptr(hd), ptr(llr_a), ptr(ord_a), B, ptr(sol), ptr(rank), ptr(piv)))
         return (sol, rank, piv) if want_pivots else (sol, rank)
 
+    def osd0_pipeline(self, syndromes, hard, post):
+        """The pipeline's OSD-0 kernels on host float32 posteriors -> (solution int8 [B, n], osd_info int32 [B])."""
+        syn = np.ascontiguousarray(syndromes, dtype=np.int8).reshape(-1, self.m)
+        hd = np.ascontiguousarray(np.asarray(hard) & 1, dtype=np.int8).reshape(-1, self.n)
+        B = syn.shape[0]
+        pf = np.ascontiguousarray(post, dtype=np.float32).reshape(B, self.n)
+        sol = np.zeros((B, self.n), dtype=np.int8)
+        info = np.zeros(B, dtype=np.int32)
+        check(load().qb_osd0_pipeline_host(self._h, ptr(syn), ptr(hd), ptr(pf), B, ptr(sol), ptr(info)))
+        return sol, info
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             load().qb_decoder_destroy(self._h)
@@ -327,6 +339,19 @@ class Pipeline:
         check(load().qb_pipeline_decode_host(self._h, ptr(sz), ptr(tz), ptr(sx), ptr(tx), B, C.byref(c), ptr(counts), ptr(flags)))
         return counts, flags
 
+    def enable_detail(self, on=True):
+        check(load().qb_pipeline_enable_detail(self._h, 1 if on else 0))
+
+    def last_batch_detail(self, side, B, want_post=True, want_info=True):
+        """(hard_bits uint32 [B, nw], posteriors float32 [B, n] or None, osd_info int32 [B] or None) of the last batch."""
+        dec = self.decX if side else self.decZ
+        nw = max(1, (dec.n + 31) // 32)
+        hard = np.zeros((B, nw), dtype=np.uint32)
+        post = np.zeros((B, dec.n), dtype=np.float32) if want_post else None
+        info = np.zeros(B, dtype=np.int32) if want_info else None
+        check(load().qb_pipeline_last_batch_detail(self._h, int(side), ptr(hard), ptr(post), ptr(info)))
+        return hard, post, info
+
     def set_stream(self, cuda_stream=None):
         """Issue the pipeline's work on ``cuda_stream`` (a cudaStream_t as int, e.g.
         ``torch.cuda.current_stream().cuda_stream``); ``None`` restores the pipeline's own stream."""
@@ -363,15 +388,62 @@ def graph_key(indptr, indices, n):
     return h.hexdigest()
 
 
-def cached_decoder(indptr, indices, n, prior):
-    """Decoder handle for a CSR graph, reused across calls (the reference API passes H every call)."""
+def cached_decoder(indptr, indices, n, prior=None):
+    """Decoder handle for a CSR graph, reused across calls (the reference API passes H every call).
+
+    ``prior=None`` is for entry points that never read the priors (OSD-0, syndrome check, single check pass):
+    the handle is reused as it is -- no prior upload, no re-layout of the per-edge plan -- so the reference's
+    per-shot pattern min-sum -> OSD (engine.py:84-97) does not flip the handle's prior back and forth."""
     key = (graph_key(indptr, indices, n), default_device())
     dec = _decoder_cache.get(key)
     if dec is None:
         if len(_decoder_cache) >= _CACHE_MAX:
             _decoder_cache.pop(next(iter(_decoder_cache))).close()
-        dec = Decoder(indptr, indices, n, prior)
+        dec = Decoder(indptr, indices, n, np.zeros(int(n)) if prior is None else prior)
         _decoder_cache[key] = dec
-    else:
+    elif prior is not None:
         dec.set_prior(prior)
+    return dec
+
+
+# The reference API hands over the dense H (or the scipy CSR) on every call; scanning 1008 x 8785 entries and hashing
+# the CSR per call would dominate a per-shot loop.  Results are memoised per array object: the key holds a weak
+# fingerprint (id, shape, dtype, data pointer) and the value keeps a reference to the array so the id cannot be
+# recycled while the entry lives.  Callers that mutate H in place between calls must pass a new array.
+_csr_cache = {}
+_CSR_CACHE_MAX = 16
+
+
+def dense_csr(H):
+    """(indptr, indices) int32 of the non-zero pattern of a dense matrix, memoised per array object."""
+    H = np.asarray(H)
+    key = (id(H), H.shape, H.dtype.str, H.__array_interface__["data"][0])
+    hit = _csr_cache.get(key)
+    if hit is not None and hit[0] is H:
+        return hit[1], hit[2]
+    mask = H != 0
+    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
+    indices = np.nonzero(mask)[1].astype(np.int32)
+    if len(_csr_cache) >= _CSR_CACHE_MAX:
+        _csr_cache.pop(next(iter(_csr_cache)))
+    _csr_cache[key] = (H, indptr, indices)
+    return indptr, indices
+
+
+_handle_by_arrays = {}
+
+
+def cached_decoder_for(indptr, indices, n, prior=None):
+    """cached_decoder() without re-hashing the CSR arrays when the same array objects come back."""
+    key = (id(indptr), id(indices), int(n), default_device())
+    hit = _handle_by_arrays.get(key)
+    if hit is not None and hit[0] is indptr and hit[1] is indices and hit[2]._h.value:
+        dec = hit[2]
+        if prior is not None:
+            dec.set_prior(prior)
+        return dec
+    dec = cached_decoder(indptr, indices, n, prior)
+    if len(_handle_by_arrays) >= _CSR_CACHE_MAX:
+        _handle_by_arrays.pop(next(iter(_handle_by_arrays)))
+    _handle_by_arrays[key] = (indptr, indices, dec)
     return dec

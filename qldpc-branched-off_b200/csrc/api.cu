@@ -118,6 +118,9 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     *out = nullptr;
     QB_REQUIRE(m >= 0 && n >= 0 && indptr && prior, "bad graph arguments");
     QB_REQUIRE(k >= 0 && k <= 32, "at most 32 logical rows are supported");
+    QB_REQUIRE(k == 0 || (lptr && lidx), "logical rows are NULL");
+    QB_REQUIRE(k == 0 || lptr[0] == 0, "logical_ptr[0] must be 0");
+    for (int b = 0; b < k; ++b) QB_REQUIRE(lptr[b + 1] >= lptr[b], "logical_ptr must be non-decreasing");
     QB_REQUIRE(indptr[0] == 0, "indptr[0] must be 0");
     for (int i = 0; i < m; ++i) QB_REQUIRE(indptr[i + 1] >= indptr[i], "indptr must be non-decreasing");
     const int nnz = indptr[m];
@@ -170,7 +173,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     std::vector<uint8_t> rexact(std::max(1, g.n_rslices), 0);
     for (int r = 0; r < m; ++r) if (indptr[r + 1] - indptr[r] == 1) rexact[r >> 5] = 1;
     g.nan_anywhere = 0;
-    for (int j = 0; j < n; ++j) if (!std::isfinite(prior[j])) g.nan_anywhere = 1;
+    for (int j = 0; j < n; ++j) if (!std::isfinite((float)prior[j])) g.nan_anywhere = 1;   // the kernels see float priors
     {   // a variable on two degree-1 rows can receive +inf and -inf -> NaN posterior: exact path everywhere
         std::vector<int> deg1(n, 0);
         for (int r = 0; r < m; ++r) if (indptr[r + 1] - indptr[r] == 1 && ++deg1[indices[indptr[r]]] > 1) d->graph_nan = 1;
@@ -235,15 +238,15 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     QB_CUDA(cudaSetDevice(dec->device));
     std::vector<float> pf(dec->g.n);
     dec->g.nan_anywhere = dec->graph_nan;
-    for (int j = 0; j < dec->g.n; ++j) { pf[j] = (float)prior[j]; if (!std::isfinite(prior[j])) dec->g.nan_anywhere = 1; }
+    for (int j = 0; j < dec->g.n; ++j) { pf[j] = (float)prior[j]; if (!std::isfinite(pf[j])) dec->g.nan_anywhere = 1; }
     if (dec->g.n) QB_CUDA(cudaMemcpy(dec->d_prior, pf.data(), sizeof(float) * pf.size(), cudaMemcpyHostToDevice));
     // the per-edge layout groups variables by prior value: rebuild it
     QB_CUDA(cudaDeviceSynchronize());
     edge_plan_destroy(dec->edge);
     dec->edge = nullptr;
-    bool finite = true;
-    for (float v : pf) if (!std::isfinite(v)) finite = false;
-    if (finite) return edge_plan_create(dec, pf.data(), &dec->edge);
+    // same predicate as qb_decoder_create: non-finite priors or a graph that can produce NaN posteriors on its own
+    // (a variable on two degree-1 rows) stay on the exact compressed-state kernel
+    if (!dec->g.nan_anywhere) return edge_plan_create(dec, pf.data(), &dec->edge);
     return QB_OK;
 }
 
@@ -477,6 +480,38 @@ int qb_osd0_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h
     return QB_OK;
 }
 
+int qb_osd0_pipeline_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h, const float *post_h, int32_t B,
+                          int8_t *solution_h, int32_t *osd_info_h)
+{
+    QB_REQUIRE(dec && syndrome_h && hard_h && post_h && solution_h, "NULL argument");
+    if (B <= 0) return QB_OK;
+    QB_CUDA(cudaSetDevice(dec->device));
+    const GraphDev &g = dec->g;
+    const size_t sB = (size_t)B;
+    if (int rc = dec->scratch.ensure(carve_size({sB * g.m, sB * g.n, sB * g.mw * 4, sB * g.nw * 4, sB * g.n * 4, sB * 4, 4}))) return rc;
+    Carver cv(dec->scratch.ptr);
+    int8_t *d_syn8 = cv.take<int8_t>(sB * g.m), *d_hard8 = cv.take<int8_t>(sB * g.n);
+    uint32_t *d_syn = cv.take<uint32_t>(sB * g.mw), *d_hard = cv.take<uint32_t>(sB * g.nw);
+    float *d_post = cv.take<float>(sB * g.n);
+    int32_t *d_info = cv.take<int32_t>(sB), *d_nfail = cv.take<int32_t>(1);
+    if (g.m) QB_CUDA(cudaMemcpy(d_syn8, syndrome_h, sB * g.m, cudaMemcpyHostToDevice));
+    if (g.n) QB_CUDA(cudaMemcpy(d_hard8, hard_h, sB * g.n, cudaMemcpyHostToDevice));
+    if (g.n) QB_CUDA(cudaMemcpy(d_post, post_h, sB * g.n * 4, cudaMemcpyHostToDevice));
+    QB_CUDA(cudaMemset(d_info, 0, sB * 4));
+    QB_CUDA(cudaMemcpy(d_nfail, &B, 4, cudaMemcpyHostToDevice));
+    if (int rc = launch_pack_bits(d_syn8, B, g.m, d_syn, g.mw, 0)) return rc;
+    if (int rc = launch_pack_bits(d_hard8, B, g.n, d_hard, g.nw, 0)) return rc;
+    OsdLaunch a{};                       // exactly what decode_batch() issues for one side, every shot in the queue
+    a.syn_bits = d_syn; a.hard_bits = d_hard; a.post = d_post; a.fail_idx = nullptr; a.F = B; a.n_fail_d = d_nfail;
+    a.rank_out = d_info; a.rank_tag = 2 << 16;
+    if (int rc = launch_osd0(dec, a, 0)) return rc;
+    if (int rc = launch_unpack_bits(d_hard, B, g.n, g.nw, d_hard8, 0)) return rc;
+    if (g.n) QB_CUDA(cudaMemcpy(solution_h, d_hard8, sB * g.n, cudaMemcpyDeviceToHost));
+    if (osd_info_h) QB_CUDA(cudaMemcpy(osd_info_h, d_info, sB * 4, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaDeviceSynchronize());
+    return QB_OK;
+}
+
 int qb_gf2_eliminate_host(int device, int64_t *A_h, int64_t *b_h, int32_t m, int32_t n, uint64_t *A_packed_h,
                           int64_t *pivot_rows_h, int64_t *pivot_cols_h, int32_t *num_pivots_h)
 {
@@ -491,22 +526,21 @@ int qb_gf2_eliminate_host(int device, int64_t *A_h, int64_t *b_h, int32_t m, int
         if (b_h[r] & 1) bp[r >> 5] |= 1u << (r & 31);
     }
     const int mn = std::min(m, n);
-    uint32_t *dA = nullptr, *db = nullptr; int32_t *dpr = nullptr, *dpc = nullptr, *dnp = nullptr;
-    QB_CUDA(cudaMalloc(&dA, Ap.size() * 4)); QB_CUDA(cudaMalloc(&db, bp.size() * 4));
-    QB_CUDA(cudaMalloc(&dpr, mn * 4)); QB_CUDA(cudaMalloc(&dpc, mn * 4)); QB_CUDA(cudaMalloc(&dnp, 4));
+    // one allocation, released on every path
+    struct DevBuf { void *p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } buf;
+    QB_CUDA(cudaMalloc(&buf.p, carve_size({Ap.size() * 4, bp.size() * 4, (size_t)mn * 4, (size_t)mn * 4, 4})));
+    Carver cv(buf.p);
+    uint32_t *dA = cv.take<uint32_t>(Ap.size()), *db = cv.take<uint32_t>(bp.size());
+    int32_t *dpr = cv.take<int32_t>(mn), *dpc = cv.take<int32_t>(mn), *dnp = cv.take<int32_t>(1);
     QB_CUDA(cudaMemcpy(dA, Ap.data(), Ap.size() * 4, cudaMemcpyHostToDevice));
     QB_CUDA(cudaMemcpy(db, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
-    int rc = launch_gf2_dense(dA, db, m, n, nw, dpr, dpc, dnp, 0);
+    if (int rc = launch_gf2_dense(dA, db, m, n, nw, dpr, dpc, dnp, 0)) return rc;
     std::vector<int32_t> pr(mn), pc(mn);
-    if (!rc) {
-        QB_CUDA(cudaMemcpy(Ap.data(), dA, Ap.size() * 4, cudaMemcpyDeviceToHost));
-        QB_CUDA(cudaMemcpy(bp.data(), db, bp.size() * 4, cudaMemcpyDeviceToHost));
-        QB_CUDA(cudaMemcpy(pr.data(), dpr, mn * 4, cudaMemcpyDeviceToHost));
-        QB_CUDA(cudaMemcpy(pc.data(), dpc, mn * 4, cudaMemcpyDeviceToHost));
-        QB_CUDA(cudaMemcpy(num_pivots_h, dnp, 4, cudaMemcpyDeviceToHost));
-    }
-    cudaFree(dA); cudaFree(db); cudaFree(dpr); cudaFree(dpc); cudaFree(dnp);
-    if (rc) return rc;
+    QB_CUDA(cudaMemcpy(Ap.data(), dA, Ap.size() * 4, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemcpy(bp.data(), db, bp.size() * 4, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemcpy(pr.data(), dpr, mn * 4, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemcpy(pc.data(), dpc, mn * 4, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemcpy(num_pivots_h, dnp, 4, cudaMemcpyDeviceToHost));
     for (int r = 0; r < m; ++r) {
         for (int c = 0; c < n; ++c) A_h[(size_t)r * n + c] = (Ap[(size_t)r * nw + (c >> 5)] >> (c & 31)) & 1u;
         b_h[r] = (bp[r >> 5] >> (r & 31)) & 1u;
@@ -578,13 +612,22 @@ int qb_syndrome_from_events(qb_sampler *s, const int32_t *ev_ptr_d, const uint32
     return launch_events_syndrome(s, ev_ptr_d, events_d, B, synZ, trueZ, synX, trueX, static_cast<cudaStream_t>(stream));
 }
 
+// host fault-event lists (CSR over shots): offsets start at 0 and never decrease, so that the kernel stays inside
+// events[0 .. ev_ptr[B]); the kernel itself ignores events whose location is >= L
+static int check_events(const qb_sampler *, const int32_t *ev_ptr_h, const uint32_t *events_h, int B)
+{
+    QB_REQUIRE(ev_ptr_h[0] == 0, "ev_ptr[0] must be 0");
+    for (int b = 0; b < B; ++b) QB_REQUIRE(ev_ptr_h[b + 1] >= ev_ptr_h[b], "ev_ptr must be non-decreasing");
+    QB_REQUIRE(ev_ptr_h[B] == 0 || events_h != nullptr, "events is NULL");
+    return QB_OK;
+}
+
 int qb_syndrome_from_events_host(qb_sampler *s, const int32_t *ev_ptr_h, const uint32_t *events_h, int32_t B,
                                  int8_t *sparseZ_h, int8_t *trueZ_h, int8_t *sparseX_h, int8_t *trueX_h)
 {
     QB_REQUIRE(s && ev_ptr_h && sparseZ_h && trueZ_h && sparseX_h && trueX_h, "NULL argument");
     if (B <= 0) return QB_OK;
-    QB_REQUIRE(ev_ptr_h[0] == 0, "ev_ptr[0] must be 0");
-    for (int b = 0; b < B; ++b) QB_REQUIRE(ev_ptr_h[b + 1] >= ev_ptr_h[b], "ev_ptr must be non-decreasing");
+    if (int rc = check_events(s, ev_ptr_h, events_h, B)) return rc;
     QB_CUDA(cudaSetDevice(s->device));
     const size_t sB = (size_t)B, nev = (size_t)ev_ptr_h[B];
     if (int rc = s->scratch.ensure(carve_size({(sB + 1) * 4, nev * 4, sB * s->mwZ * 4, sB * s->mwX * 4, sB * 4, sB * 4,
@@ -639,6 +682,9 @@ struct qb_pipeline {
     int64_t *counts = nullptr;   // device [8]
     int32_t *ev_ptr = nullptr; uint32_t *events = nullptr; size_t ev_cap = 0;
     int8_t *syn8 = nullptr;      // staging for decode_host
+    int32_t *osdinfoZ = nullptr, *osdinfoX = nullptr;   // per shot: pivots used | OSD path << 16 (detail mode only)
+    int detail = 0;              // qb_pipeline_enable_detail
+    int last_B = 0;              // shots of the last batch (what qb_pipeline_last_batch_detail may read)
     std::vector<void *> owned;
     std::vector<cudaEvent_t> evs;
     qb_pipeline_stats stats{};
@@ -682,7 +728,12 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
     cudaStream_t st = p->st;
     const bool timed = batch_no < MAX_TIMED_BATCHES;
     cudaEvent_t *ev = timed ? &p->evs[(size_t)batch_no * EV_PER_BATCH] : nullptr;
+    p->last_B = B;
     QB_CUDA(cudaMemsetAsync(p->nfail, 0, 2 * sizeof(int32_t), st));
+    if (p->detail) {
+        QB_CUDA(cudaMemsetAsync(p->osdinfoZ, 0, (size_t)B * sizeof(int32_t), st));
+        QB_CUDA(cudaMemsetAsync(p->osdinfoX, 0, (size_t)B * sizeof(int32_t), st));
+    }
     for (int side = 0; side < 2; ++side) {
         qb_decoder *d = side ? p->dx : p->dz;
         MinsumLaunch a{};
@@ -710,6 +761,7 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
             a.syn_bits = side ? p->synX : p->synZ; a.hard_bits = side ? p->hardX : p->hardZ;
             a.post = side ? p->postX : p->postZ; a.fail_idx = side ? p->sortX : p->sortZ;
             a.F = B; a.n_fail_d = p->nfail + side;
+            if (p->detail) { a.rank_out = side ? p->osdinfoX : p->osdinfoZ; a.rank_tag = 2 << 16; }
             if (int rc = launch_osd0(d, a, ss)) return rc;
             p->stats.kernel_launches++;
         }
@@ -777,6 +829,7 @@ int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_
     AL(convZ, B) AL(convX, B) AL(flags, B) AL(itZ, B) AL(itX, B) AL(failZ, B) AL(failX, B) AL(nfail, 2)
     AL(fwZ, B) AL(fwX, B) AL(sortZ, B) AL(sortX, B)
     AL(postZ, B * gz.n) AL(postX, B * gx.n) AL(counts, 8) AL(ev_ptr, B + 1) AL(syn8, B * std::max(gz.m, gx.m))
+    AL(osdinfoZ, B) AL(osdinfoX, B)
 #undef AL
     if (!rc) {
         p->evs.resize((size_t)MAX_TIMED_BATCHES * EV_PER_BATCH);
@@ -844,6 +897,7 @@ int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const u
     QB_CUDA(cudaSetDevice(p->dz->device));
     p->stats = qb_pipeline_stats{};
     if (B == 0) { memset(counts_h, 0, 8 * sizeof(int64_t)); return QB_OK; }
+    if (int rc = check_events(p->s, ev_ptr_h, events_h, B)) return rc;
     const size_t nev = (size_t)ev_ptr_h[B];
     if (nev > p->ev_cap) {
         if (p->events) cudaFree(p->events);
@@ -897,6 +951,30 @@ int qb_pipeline_decode_host(qb_pipeline *p, const int8_t *sparseZ_h, const uint3
     if (int rc = decode_batch(p, B, cfg, 0)) return rc;
     if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, p->flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
     return finish_run(p, 1, counts_h);
+}
+
+int qb_pipeline_enable_detail(qb_pipeline *p, int on)
+{
+    QB_REQUIRE(p != nullptr, "NULL argument");
+    p->detail = on ? 1 : 0;
+    return QB_OK;
+}
+
+int qb_pipeline_last_batch_detail(qb_pipeline *p, int32_t side, uint32_t *hard_bits_h, float *post_h, int32_t *osd_info_h)
+{
+    QB_REQUIRE(p != nullptr && (side == 0 || side == 1), "bad argument");
+    QB_CUDA(cudaSetDevice(p->dz->device));
+    QB_CUDA(cudaStreamSynchronize(p->st));
+    const size_t B = (size_t)p->last_B;
+    if (B == 0) return QB_OK;
+    const GraphDev &g = side ? p->dx->g : p->dz->g;
+    if (hard_bits_h) QB_CUDA(cudaMemcpy(hard_bits_h, side ? p->hardX : p->hardZ, B * g.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (post_h) QB_CUDA(cudaMemcpy(post_h, side ? p->postX : p->postZ, B * g.n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (osd_info_h) {
+        QB_REQUIRE(p->detail, "per-shot OSD information is recorded only after qb_pipeline_enable_detail(p, 1)");
+        QB_CUDA(cudaMemcpy(osd_info_h, side ? p->osdinfoX : p->osdinfoZ, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return QB_OK;
 }
 
 int qb_pipeline_last_stats(qb_pipeline *p, qb_pipeline_stats *out)

@@ -83,7 +83,7 @@ struct qb_decoder {
     int alpha_cap = 0;
     qb::Scratch scratch;        // host-API staging
     qb::Scratch work;           // kernel workspaces (general min-sum messages, OSD spill)
-    qb::Scratch ovf;            // OSD: sides the one-warp kernel hands to the four-warp kernel (count + list)
+    qb::Scratch ovf;            // OSD: workspaces of the free-row path (candidate lists, records, overflow queue)
     int sm_count = 148;
     int max_smem_optin = 0;
     qb::EdgePlan *edge = nullptr;   // nullptr: graph does not fit the per-edge kernel
@@ -136,12 +136,15 @@ struct OsdLaunch {
     const int32_t *fail_idx;    // nullable: indices into the batch; nullptr = all of 0..F-1
     int F;                      // number of sides (upper bound when n_fail_d given)
     const int32_t *n_fail_d;    // nullable device count
-    int32_t *rank_out;          // nullable [B]
+    int32_t *rank_out;          // nullable [B]: pivots used | rank_tag
+    int rank_tag;               // OR-ed into rank_out (the pipeline marks which kernel solved the side: path << 16)
     int32_t *pivots_out;        // nullable [B][min(m,n)]
     int exact_rows;             // emulate the reference's pivot-row order (inconsistent syndromes)
 };
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
-int launch_osd0_warp(qb_decoder *dec, const OsdLaunch &a, int32_t *overflow_count_d, int32_t *overflow_idx_d, int *used, cudaStream_t st);
+// free-row elimination path (osd_free.cu): applicable to graphs with column signatures (column degree <= 8)
+bool osd_free_applicable(const qb_decoder *dec);
+int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d, int32_t **ovf_idx_d, cudaStream_t st);
 // order the failure queue by descending residual weight (longest elimination first)
 int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail_d, int32_t *sorted_idx, cudaStream_t st);
 

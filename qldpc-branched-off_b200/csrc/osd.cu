@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(OSD_THREADS, OSD_CTAS_PER_SM) osd0_kernel(OsdA
         if (P.a.pivots_out)
             for (int i = tid; i < P.rank_cap; i += blockDim.x)
                 P.a.pivots_out[(size_t)shot * P.rank_cap + i] = i < t ? (int)piv_pos[i] : -1;
-        if (P.a.rank_out && tid == 0) P.a.rank_out[shot] = t;
+        if (P.a.rank_out && tid == 0) P.a.rank_out[shot] = t | P.a.rank_tag;
 #ifdef QB_OSD_PROFILE
         if (tid == 0) {
             const int slot = atomicAdd(&g_osd_prof_n, 1);
@@ -605,17 +605,18 @@ int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
     }
     if (!a.ordering && !a.post) { set_error("OSD-0 needs posteriors or an ordering"); return QB_ERR_ARG; }
     const int wpl = ceil_div(g.mw, 32);
-    const char *warp_opt = getenv("QLDPC_B200_OSD_WARP");
-    if (warp_opt && warp_opt[0] == '1' && !a.exact_rows && a.n_fail_d && a.fail_idx) {
-        // opt-in experiment: one warp per side (osd_warp.cu); the four-warp kernel below only takes what it hands back
-        if (int rc = dec->ovf.ensure(((size_t)a.F + 64) * sizeof(int32_t))) return rc;
-        int32_t *cnt = dec->ovf.as<int32_t>(), *idx = cnt + 64;
-        int used = 0;
-        if (int rc = launch_osd0_warp(dec, a, cnt, idx, &used, st)) return rc;
-        if (used) {
-            OsdLaunch b = a;
-            b.fail_idx = idx; b.n_fail_d = cnt;
-            return launch_osd_wpl<1, false>(dec, b, st);
+    if (!a.exact_rows && !a.ordering && osd_free_applicable(dec)) {
+        // pipeline path: selection + free-row elimination (osd_free.cu); the full-width kernel below takes what that
+        // hands back (more free rows / touched rows / candidates than it provides for), normally ~1 % of the sides
+        int32_t *ovf_count = nullptr, *ovf_idx = nullptr;
+        if (int rc = launch_osd0_free(dec, a, &ovf_count, &ovf_idx, st)) return rc;
+        OsdLaunch b = a;
+        b.fail_idx = ovf_idx; b.n_fail_d = ovf_count;
+        switch (wpl) {
+            case 1: return launch_osd_wpl<1, false>(dec, b, st);
+            case 2: return launch_osd_wpl<2, false>(dec, b, st);
+            case 3: return launch_osd_wpl<3, false>(dec, b, st);
+            default: return launch_osd_wpl<4, false>(dec, b, st);
         }
     }
     if (a.exact_rows) {

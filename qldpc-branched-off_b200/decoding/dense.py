@@ -6,11 +6,9 @@ from .sparse import _alpha_dispatch
 
 
 def _csr_of(H):
-    H = np.asarray(H)
-    mask = H != 0
-    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
-    indices = np.nonzero(mask)[1].astype(np.int32)
-    return indptr, indices
+    """CSR pattern of the dense matrix, memoised per array object (the reference engine passes the same
+    ``shared_data['HdecZ']`` on every call, engine.py:90-97)."""
+    return _lib.dense_csr(H)
 
 
 def performMinSum_Symmetric(H, syndrome, initialBelief, maxIter=50, alpha=1.0, alpha_mode="dynamical", damping=1.0,
@@ -23,7 +21,7 @@ def performMinSum_Symmetric(H, syndrome, initialBelief, maxIter=50, alpha=1.0, a
     prior = np.asarray(initialBelief, dtype=np.float64)
     syndrome = np.asarray(syndrome, dtype=np.int8)
     indptr, indices = _csr_of(H)
-    dec = _lib.cached_decoder(indptr, indices, n, prior)
+    dec = _lib.cached_decoder_for(indptr, indices, n, prior)
     if alpha_estimation:
         if maxIter < 1:
             return np.zeros(n, dtype=np.int8), False, None, -1
@@ -42,6 +40,6 @@ def performBeliefPropagationFast(H, syndrome, initialBelief, maxIter=50):
     H = np.asarray(H)
     prior = np.asarray(initialBelief, dtype=np.float64)
     indptr, indices = _csr_of(H)
-    dec = _lib.cached_decoder(indptr, indices, H.shape[1], prior)
+    dec = _lib.cached_decoder_for(indptr, indices, H.shape[1], prior)
     hard, conv, values, fin = dec.bp(np.asarray(syndrome, dtype=np.int8)[None, :], maxIter)
     return hard[0], bool(conv[0]), values[0], int(fin[0])

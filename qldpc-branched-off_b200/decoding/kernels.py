@@ -17,7 +17,7 @@ from .. import _lib
 
 
 def _decoder(H_indices, H_indptr, n, prior):
-    return _lib.cached_decoder(H_indptr, H_indices, n, prior)
+    return _lib.cached_decoder_for(H_indptr, H_indices, n, prior)
 
 
 def minsum_decoder_full(H_indices, H_indptr, syndrome, initialBelief, maxIter, use_dynamic_alpha, alpha_val,
@@ -41,7 +41,7 @@ def minsum_decoder_full_autoregressive(H_indices, H_indptr, syndrome, initialBel
 
 
 def minsum_core_sparse(H_data, H_indices, H_indptr, Q_flat, syndrome_sign, alpha, m, n):
-    dec = _decoder(H_indices, H_indptr, n, np.zeros(n))
+    dec = _decoder(H_indices, H_indptr, n, None)
     R, Rs = dec.minsum_core(np.asarray(Q_flat, dtype=np.float64)[None, :],
                             np.asarray(syndrome_sign, dtype=np.float64)[None, :], float(alpha))
     return R[0], Rs[0]
@@ -49,7 +49,7 @@ def minsum_core_sparse(H_data, H_indices, H_indptr, Q_flat, syndrome_sign, alpha
 
 def syndrome_check(H_data, H_indices, H_indptr, candidate, m):
     n = len(candidate)
-    dec = _decoder(H_indices, H_indptr, n, np.zeros(n))
+    dec = _decoder(H_indices, H_indptr, n, None)
     return dec.syndrome_check(np.asarray(candidate, dtype=np.int8)[None, :])[0]
 
 

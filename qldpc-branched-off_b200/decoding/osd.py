@@ -22,7 +22,7 @@ def performOSD_enhanced(H, syndrome, llr, hard, order=0, max_combinations=None, 
     syndrome = np.asarray(syndrome)
     hard = np.asarray(hard)
     indptr, indices = _csr_of(H)
-    dec = _lib.cached_decoder(indptr, indices, n, np.zeros(n))
+    dec = _lib.cached_decoder_for(indptr, indices, n)          # OSD-0 never reads the priors: reuse the handle as is
     sol, _ = dec.osd0((syndrome.astype(np.int64) & 1).astype(np.int8)[None, :], hard[None, :],
                       llr=None if ordering is not None else np.asarray(llr, dtype=np.float64)[None, :],
                       ordering=None if ordering is None else np.asarray(ordering)[None, :])

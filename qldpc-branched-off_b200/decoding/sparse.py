@@ -28,7 +28,7 @@ def performMinSum_Symmetric_Sparse(H_csr, syndrome, initialBelief, maxIter=100, 
     values float64[n], final_iter int).  Messages are float32 on the device."""
     mode, aval, seq = _alpha_dispatch(alpha, alpha_mode)
     prior = np.asarray(initialBelief, dtype=np.float64)
-    dec = _lib.cached_decoder(H_csr.indptr, H_csr.indices, H_csr.shape[1], prior)
+    dec = _lib.cached_decoder_for(H_csr.indptr, H_csr.indices, H_csr.shape[1], prior)
     hard, conv, values, fin = dec.minsum(np.asarray(syndrome, dtype=np.int8)[None, :], maxIter, mode, alpha=aval,
                                          alpha_seq=seq, damping=damping, clip_llr=clip_llr)
     return hard[0], bool(conv[0]), values[0], int(fin[0])
@@ -39,5 +39,5 @@ def performMinSum_Symmetric_Sparse_batch(H_csr, syndromes, initialBelief, maxIte
     """Batched form: syndromes int8 [B, m] -> (hard int8 [B, n], converged bool [B], values f64 [B, n], final_iter [B])."""
     mode, aval, seq = _alpha_dispatch(alpha, alpha_mode)
     prior = np.asarray(initialBelief, dtype=np.float64)
-    dec = _lib.cached_decoder(H_csr.indptr, H_csr.indices, H_csr.shape[1], prior)
+    dec = _lib.cached_decoder_for(H_csr.indptr, H_csr.indices, H_csr.shape[1], prior)
     return dec.minsum(syndromes, maxIter, mode, alpha=aval, alpha_seq=seq, damping=damping, clip_llr=clip_llr)

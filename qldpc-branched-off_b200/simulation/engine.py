@@ -177,6 +177,10 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
     stop_on_errors = target_logical_errors is not None and target_logical_errors > 0
 
     dist, rank, world = _dist()
+    if dist is not None and _dist_backend(dist) == "nccl":
+        import torch
+        torch.cuda.set_device(_lib.default_device())
+    base_seed = _broadcast_seed(dist, base_seed)
     if batch_size is None:
         batch_size = int(min(65536, max(256, -(-max_trials // world))))
     eng = ShotEngine(compiled, Lx, Lz, matrices, max_batch=batch_size)
@@ -213,11 +217,34 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
     return result
 
 
+def _dist_backend(dist):
+    return dist.get_backend()
+
+
+def _collective_device(dist):
+    """Tensors for a collective live on this rank's own GPU under NCCL (LOCAL_RANK, like every handle of the
+    package), on the host under gloo."""
+    import torch
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", _lib.default_device())
+    return torch.device("cpu")
+
+
+def _broadcast_seed(dist, seed):
+    """Every rank must key Philox with the same seed (rank 0's draw when the caller passed None)."""
+    if dist is None:
+        return seed
+    import torch
+    t = torch.tensor([int(seed)], dtype=torch.int64, device=_collective_device(dist))
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
 def _reduce_counts(dist, counts):
     if dist is None:
         return counts
     import torch
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    dev = _collective_device(dist)
     t = torch.from_numpy(np.asarray(counts, dtype=np.int64).copy()).to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
@@ -227,7 +254,7 @@ def _gather_flags(dist, world, flags, round_total):
     if dist is None:
         return flags
     import torch
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    dev = _collective_device(dist)
     width = -(-round_total // world)
     buf = np.full(width, 255, dtype=np.uint8)       # 255 = padding marker
     buf[:len(flags)] = flags

@@ -213,7 +213,7 @@ def test_osd0_bit_exact_for_supplied_orderings(tag):
         assert sol.dtype == np.int64
         assert np.array_equal(sol, unpack(g[f"osd_sol_{sd}"], n)), "OSD-0 must equal the reference for its own ordering"
         assert np.array_equal(dec.syndrome_check(sol.astype(np.int8)), syn)
-        assert (rank < np.linalg.matrix_rank(H[:, :400]) + 10**9).all()
+        assert ((rank > 0) & (rank <= min(H.shape))).all(), "pivots needed: at least one, at most min(m, n)"
         dec.close()
 
 
@@ -391,29 +391,6 @@ def test_pipeline_full_size_properties_gross():
     assert np.array_equal(dec.syndrome_check(sol.astype(np.int8)), syn[~conv])
     assert rank.max() <= 1008 and rank.mean() < 600, "early termination should need far fewer than rank(H) pivots"
     dec.close()
-
-
-def test_osd_one_warp_kernel_matches_default_kernel():
-    """The opt-in one-warp-per-side OSD-0 kernel (osd_warp.cu, QLDPC_B200_OSD_WARP=1) gives the flags of the default
-    four-warp kernel on the gross and the 72-qubit code (shared-memory-resident and spilled stored columns)."""
-    from qldpc_b200.simulation.engine import ShotEngine
-    for tag, p, shots in (("144", 0.005, 3000), ("72", 0.006, 4000)):
-        s = code_setup(tag); M = matrices(tag, p)
-        cfg = _lib.make_config(20, _lib.QB_ALPHA_DYNAMIC)
-        outs = []
-        for env in ({}, {"QLDPC_B200_OSD_WARP": "1", "QLDPC_B200_OSD_WARP_SIDES": "8"},
-                    {"QLDPC_B200_OSD_WARP": "1", "QLDPC_B200_OSD_WARP_SIDES": "24"}):
-            os.environ.update(env)
-            try:
-                eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=2048)
-                outs.append(eng.pipeline.run(7, 0, shots, p, cfg, want_flags=True))
-                eng.close()
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
-        assert outs[0][0][4] > 0
-        for c, f in outs[1:]:
-            assert np.array_equal(c, outs[0][0]) and np.array_equal(f, outs[0][1])
 
 
 def test_run_simulation_api_and_early_stop():
