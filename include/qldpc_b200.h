@@ -144,6 +144,12 @@ int qb_osd0_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h
 int qb_osd0_pipeline_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h, const float *post_h, int32_t B,
                           int8_t *solution_h, int32_t *osd_info_h);
 
+/* Accounting of the pipeline's OSD-0 path on this decoder since the previous call (read and cleared):
+ * out10_h[0..4] = sides that left the first tier of the free-row elimination kernel because of { candidate window
+ * exhausted, touched-row capacity, free-slot capacity, record buffer, window not materialised }, out10_h[5..9] the
+ * same for the second tier (those sides are solved by the full-width kernel).  Replaces nothing in the reference. */
+int qb_decoder_osd_stats(qb_decoder *dec, int32_t *out10_h);
+
 /* Dense GF(2) Gauss-Jordan of an arbitrary m x n 0/1 matrix with right-hand side:
  * gf2_elimination (src/decoding/kernels.py:6-34) and gf2_elimination_packed (:98-106).
  * A_h int64 [m][n] and b_h int64 [m] are reduced in place (the reference mutates them);

@@ -44,7 +44,7 @@ EXPORTS = [
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
     "qb_pipeline_decode_host", "qb_pipeline_last_stats", "qb_pipeline_enable_detail", "qb_pipeline_last_batch_detail",
-    "qb_osd0_pipeline_host",
+    "qb_osd0_pipeline_host", "qb_decoder_osd_stats",
 ]
 
 
@@ -197,6 +197,13 @@ class Decoder:
         piv = np.full((B, rcap), -1, dtype=np.int32) if want_pivots else None
         check(load().qb_osd0_host(self._h, ptr(syn), ptr(hd), ptr(llr_a), ptr(ord_a), B, ptr(sol), ptr(rank), ptr(piv)))
         return (sol, rank, piv) if want_pivots else (sol, rank)
+
+    def osd_stats(self):
+        """Tier exits of the free-row OSD kernel since the last call, by reason (qb_decoder_osd_stats)."""
+        out = np.zeros(10, dtype=np.int32)
+        check(load().qb_decoder_osd_stats(self._h, ptr(out)))
+        names = ("window", "rows", "slots", "records", "not_materialised")
+        return {"tier_a": dict(zip(names, out[:5].tolist())), "tier_b": dict(zip(names, out[5:].tolist()))}
 
     def osd0_pipeline(self, syndromes, hard, post):
         """The pipeline's OSD-0 kernels on host float32 posteriors -> (solution int8 [B, n], osd_info int32 [B])."""

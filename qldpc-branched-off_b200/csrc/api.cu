@@ -480,6 +480,13 @@ int qb_osd0_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h
     return QB_OK;
 }
 
+int qb_decoder_osd_stats(qb_decoder *dec, int32_t *out10_h)
+{
+    QB_REQUIRE(dec && out10_h, "NULL argument");
+    QB_CUDA(cudaSetDevice(dec->device));
+    return osd_free_stats(dec, out10_h);
+}
+
 int qb_osd0_pipeline_host(qb_decoder *dec, const int8_t *syndrome_h, const int8_t *hard_h, const float *post_h, int32_t B,
                           int8_t *solution_h, int32_t *osd_info_h)
 {

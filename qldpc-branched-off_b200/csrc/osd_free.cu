@@ -42,21 +42,47 @@ constexpr int SELF_SHIFT = 17;
 constexpr int SELF_BASE = (127 - 25) << 6;
 constexpr int FREE_WARPS = 4;              // independent sides per CTA of the elimination kernel (fewer when a side's state is large)
 
+// counters[]: 0 select queue, 1 tier-A queue, 2 tier-B queue, 3 tier-A overflow count (= tier-B input), 4 tier-B overflow
+// count (= input of the full-width kernel), 5 second-selection queue, 6 tier-A window exits (= its input), 8.. statistics: 8 window exhausted, 9 touched rows, 10 free slots, 11 records,
+// 12 not materialised
+enum { CNT_SEL = 0, CNT_A = 1, CNT_B = 2, CNT_OVF_A = 3, CNT_OVF_B = 4, CNT_SEL2 = 5, CNT_WIN_A = 6, CNT_STAT = 8, CNT_STAT_B = 16, CNT_WORDS = 24 };
+
 struct OsdFreeArgs {
     GraphDev g;
     OsdLaunch a;
     int F;                       // queue length bound (n_fail_d gives the exact count when set)
-    int cap, sel_min;            // candidates materialised per side: window closed at >= sel_min, never above cap
-    int rcap;                    // compact rows per side (T capacity)
-    int fw_bits;                 // free slots per side = 128 * Q
-    int rec_cap;                 // record words per warp slot
+    int cap;                     // candidates materialised per side at most (= stride of cand)
+    int cap_per_wt;              // a side of residual weight wt gets the next power of two >= cap_per_wt * wt (512 .. cap)
+    int max_wt;                  // heavier residuals are not materialised (more free rows than any tier has slots)
     uint16_t *cand;              // [F][cap] column ids, ascending (|posterior|, index)
     int32_t *ncand;              // [F] candidates materialised; -1: hand the side to the full-width kernel
     uint32_t *res;               // [F][mw] residual syndrome
+    int32_t *counters;           // [CNT_WORDS]
+    // second selection pass (sides whose first window was exhausted in tier A, or that could not be cut into a window):
+    // the positions listed in sel_q get ALL columns in order; entry i of the list owns cand[i][cap] / ncand[i] of this
+    // pass's buffers and win_slot[position] = i tells tier B where to read
+    const int32_t *sel_count;    // nullptr: first pass over the whole failure queue
+    const int32_t *sel_q;
+    int sel_counter;             // index into counters[] of the pass's work counter
+    int sel_max;                 // entries of sel_q the second pass has buffers for
+    int32_t *win_slot;           // [F] -1, or the side's entry in the second pass's buffers
+    int32_t *win_list;           // positions wanting the second pass (appended by pass 1 and by tier A; counters[CNT_WIN_A])
+    const uint16_t *cand2; const int32_t *ncand2; int cap2;     // second-pass buffers as seen by the elimination tiers
+};
+
+// one tier of the elimination kernel: sizes of a side's state and where its sides come from / overflow to
+struct OsdFreeTier {
+    int rcap;                    // compact rows per side (T capacity)
+    int rec_cap;                 // record words per warp slot
     uint32_t *rec;               // [slots][rec_cap]  frozen transform rows, appended per pivot
     uint32_t *meta;              // [slots][rcap]     column | sigma << 16 | words << 17 per pivot
-    int32_t *counters;           // [0] select queue, [1] elimination queue, [2] overflow count
-    int32_t *ovf_idx;            // overflow queue (shot indices)
+    int queue_counter;           // index into counters[] of this tier's work counter
+    const int32_t *in_count;     // nullptr: the failure queue itself (positions 0 .. F-1); else *in_count entries of in_q
+    const int32_t *in_q;         // queue positions handed over by the previous tier
+    int out_counter;             // index into counters[] of this tier's overflow count
+    int32_t *out_list;           // overflow: queue positions (out_shots == 0) or shot indices (out_shots == 1)
+    int out_shots;
+    int32_t *win_list;           // nullable: positions whose window was exhausted are also listed here (counters[CNT_WIN_A])
 };
 
 __device__ __forceinline__ int self_bin(uint32_t key) { return min(max((int)(key >> SELF_SHIFT) - SELF_BASE, 0), SELF_BINS - 1); }
@@ -69,18 +95,20 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                 // [SELF_BINS] count; later offset << 16 | count
     uint32_t *listK = hist + SELF_BINS;                                       // [cap]
     uint16_t *listI = reinterpret_cast<uint16_t *>(listK + P.cap);            // [cap]
-    uint16_t *ord = listI + P.cap;                                            // [cap]
-    uint32_t *sv = reinterpret_cast<uint32_t *>(ord + P.cap);                 // [mw]
+    uint32_t *sv = reinterpret_cast<uint32_t *>(listI + P.cap);               // [mw]
     __shared__ int s_q, s_b1, s_b2, s_wsum[SELF_THREADS / 32], s_wt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n, mw = g.mw;
     const int F = P.a.n_fail_d ? min(*P.a.n_fail_d, P.F) : P.F;
+    const int n_in = P.sel_count ? min(min(*P.sel_count, F), P.sel_max) : F;
+    const bool second = P.sel_q != nullptr;
 
     while (true) {
-        if (tid == 0) { s_q = atomicAdd(&P.counters[0], 1); s_b1 = SELF_BINS - 1; s_b2 = -1; s_wt = 0; }
+        if (tid == 0) { s_q = atomicAdd(&P.counters[P.sel_counter], 1); s_b1 = SELF_BINS - 1; s_b2 = -1; s_wt = 0; }
         __syncthreads();
-        const int q = s_q;
-        if (q >= F) break;
+        const int qi = s_q;
+        if (qi >= n_in) break;
+        const int q = P.sel_q ? P.sel_q[qi] : qi;
         const int shot = P.a.fail_idx ? P.a.fail_idx[q] : q;
         const uint32_t *hard = P.a.hard_bits + (size_t)shot * g.nw;
         const float *post = P.a.post + (size_t)shot * n;
@@ -110,13 +138,13 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
             for (int u = 0; u < 8; ++u) if (kb[u] != 0xFFFFFFFFu) atomicAdd(&hist[kb[u]], 1u);
         }
         __syncthreads();
-        {   // weight of the residual: more free rows than the elimination kernel has slots -> full-width kernel
+        {   // weight of the residual: sizes the window (the candidates an elimination examines grow with it)
             int wt = 0;
             for (int w = tid; w < mw; w += SELF_THREADS) { const uint32_t x = sv[w]; wt += __popc(x); P.res[(size_t)q * mw + w] = x; }
             wt = __reduce_add_sync(0xFFFFFFFFu, wt);
             if (lane == 0 && wt) atomicAdd(&s_wt, wt);
         }
-        // ---- window [0, hi]: closed at >= sel_min candidates, never above cap (block-wide scan over the bins) ----
+        // ---- window [0, hi]: closed at >= sel_min candidates, never above the side's cap (block-wide scan over the bins) ----
         constexpr int BPT = SELF_BINS / SELF_THREADS;
         uint32_t c[BPT];
         uint32_t local = 0;
@@ -127,16 +155,21 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
         if (lane == 31) s_wsum[warp] = (int)inc;
         __syncthreads();
+        const int wt_side = s_wt;
+        int cap_side = 512;
+        while (cap_side < P.cap && cap_side < P.cap_per_wt * wt_side) cap_side <<= 1;
+        cap_side = second ? P.cap : min(cap_side, P.cap);
+        const int sel_min = second ? cap_side : cap_side - (cap_side >> 3);     // second pass: every column
         uint32_t run = inc - local;
         for (int w = 0; w < warp; ++w) run += (uint32_t)s_wsum[w];
-        int b1 = SELF_BINS - 1, b2 = -1;                       // first bin reaching sel_min / last bin within cap
+        int b1 = SELF_BINS - 1, b2 = -1;                       // first bin reaching sel_min / last bin within the cap
 #pragma unroll
         for (int i = 0; i < BPT; ++i) {
             const int b = tid * BPT + i;
             hist[b] = (min(run, 65535u) << 16) | min(c[i], 65535u);
             run += c[i];
-            if ((int)run >= P.sel_min) b1 = min(b1, b);
-            if ((int)run <= P.cap) b2 = b;
+            if ((int)run >= sel_min) b1 = min(b1, b);
+            if ((int)run <= cap_side) b2 = b;
         }
         b1 = __reduce_min_sync(0xFFFFFFFFu, b1); b2 = __reduce_max_sync(0xFFFFFFFFu, b2);
         if (lane == 0) { atomicMin(&s_b1, b1); atomicMax(&s_b2, b2); }
@@ -144,9 +177,12 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         const int hi = min(s_b1, s_b2);
         int M = 0;
         if (hi >= 0) { const uint32_t h = hist[hi]; M = (int)(h >> 16) + (int)(h & 0xFFFFu); }
-        const bool too_heavy = s_wt > P.fw_bits;
-        if (M == 0 || too_heavy) {                            // first bin alone exceeds the window (mass ties), or too many free rows
-            if (tid == 0) P.ncand[q] = -1;
+        const int oi = second ? qi : q;                       // entry of this pass's output buffers
+        if (M == 0 || wt_side > P.max_wt) {                   // first bin alone exceeds the window (mass ties), or too many free rows
+            if (tid == 0) {
+                P.ncand[oi] = -1;
+                if (M == 0 && !second && wt_side <= P.max_wt) P.win_list[atomicAdd(&P.counters[CNT_WIN_A], 1)] = q;   // full order in pass 2
+            }
             __syncthreads();
             continue;
         }
@@ -167,6 +203,7 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
             }
         }
         __syncthreads();
+        uint16_t *out = P.cand + (size_t)oi * P.cap;
         for (int i = tid; i < M; i += SELF_THREADS) {
             const uint32_t key = listK[i];
             const uint16_t id = listI[i];
@@ -178,61 +215,67 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
                 const uint32_t kk = listK[k];
                 rank += (kk < key) || (kk == key && listI[k] < id);
             }
-            ord[rank] = id;
+            out[rank] = id;
         }
-        __syncthreads();
-        uint16_t *out = P.cand + (size_t)q * P.cap;
-        for (int i = tid; i < M; i += SELF_THREADS) out[i] = ord[i];
-        if (tid == 0) P.ncand[q] = M;
+        if (tid == 0) { P.ncand[oi] = M; if (second) P.win_slot[q] = qi; }
         __syncthreads();
     }
 }
 
 // ---- elimination ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t u4_word(const uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-// Q = uint4 per vector (128 * Q free slots)
+__host__ __device__ inline size_t free_per_warp_bytes(int m, int rcap, int Q)
+{
+    const int m_pad16 = (m + 7) & ~7;
+    return ((size_t)rcap * 16 * Q + 512 + (size_t)m_pad16 * 2 + (size_t)((rcap + 31) / 32) * 4 + 64 + 15) & ~(size_t)15;
+}
+
+// Q = uint4 per vector (128 * Q free slots).  Lane roles: in the gather layout lane = (row slot k, word w) of the candidate's
+// signature; lanes 0 .. 4Q-1 additionally own word `lane` of the transformed syndrome (sl) and of the slot-in-use mask (ul).
+// (Q = 3: 384 slots, 12 words per vector in a 16-lane group)
 template <int Q>
-__global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_constant__ OsdFreeArgs P)
+__global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_constant__ OsdFreeArgs P, const __grid_constant__ OsdFreeTier Tr)
 {
     constexpr int WV = 4 * Q;                 // words per vector
-    constexpr int LV = WV;                    // lanes per vector in the gather layout (Q = 1, 2 -> 4, 8)
+    constexpr int LV = Q == 1 ? 4 : (Q == 2 ? 8 : 16);   // lanes per vector in the gather layout (power of two >= WV)
     constexpr int KP = 32 / LV;               // rows gathered per pass
     constexpr int PASSES = 8 / KP;
+    constexpr uint32_t WVMASK = (1u << WV) - 1u;
     const GraphDev &g = P.g;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m_pad16 = (g.m + 7) & ~7;       // rowmap entries, multiple of 8 (16-byte fills)
-    const size_t per_warp = ((size_t)m_pad16 * 2 + (size_t)P.rcap * 16 * Q + 512 + 64 + (size_t)(P.rcap / 32) * 4 + 15) & ~(size_t)15;
-    unsigned char *base = smem_raw + per_warp * warp;
+    unsigned char *base = smem_raw + free_per_warp_bytes(g.m, Tr.rcap, Q) * warp;
     uint4 *T4 = reinterpret_cast<uint4 *>(base);                                       // [rcap][Q]
     uint32_t *Tw = reinterpret_cast<uint32_t *>(base);
-    uint4 *sigbuf = reinterpret_cast<uint4 *>(base + (size_t)P.rcap * 16 * Q);         // [32] signatures of the current batch
+    uint4 *sigbuf = reinterpret_cast<uint4 *>(base + (size_t)Tr.rcap * 16 * Q);        // [32] signatures of the current batch
     const uint16_t *sig16 = reinterpret_cast<const uint16_t *>(sigbuf);
     uint16_t *rowmap = reinterpret_cast<uint16_t *>(sigbuf + 32);                      // [m_pad16] original row -> compact row
-    uint32_t *ybits = reinterpret_cast<uint32_t *>(rowmap + m_pad16);                  // [rcap / 32]
+    uint32_t *ybits = reinterpret_cast<uint32_t *>(rowmap + m_pad16);                  // [ceil(rcap / 32)]
     const int slot_id = blockIdx.x * (blockDim.x >> 5) + warp;
-    uint32_t *rec = P.rec + (size_t)slot_id * P.rec_cap;
-    uint32_t *meta = P.meta + (size_t)slot_id * P.rcap;
+    uint32_t *rec = Tr.rec + (size_t)slot_id * Tr.rec_cap;
+    uint32_t *meta = Tr.meta + (size_t)slot_id * Tr.rcap;
     const int F = P.a.n_fail_d ? min(*P.a.n_fail_d, P.F) : P.F;
+    const int n_in = Tr.in_count ? min(*Tr.in_count, F) : F;
     const int mw = g.mw;
     const int k_of_lane = lane / LV, w_of_lane = lane % LV;
+    const uint16_t *colsig16 = reinterpret_cast<const uint16_t *>(g.colsig);
 
     while (true) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(&P.counters[1], 1);
-        q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        if (q >= F) break;
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(&P.counters[Tr.queue_counter], 1);
+        qi = __shfl_sync(0xFFFFFFFFu, qi, 0);
+        if (qi >= n_in) break;
+        const int q = Tr.in_q ? Tr.in_q[qi] : qi;
         const int shot = P.a.fail_idx ? P.a.fail_idx[q] : q;
-        const int M = P.ncand[q];
-        bool overflow = M < 0;
+        const int ws = P.win_slot[q];                            // >= 0: the second selection pass re-listed this side
+        const int M = ws >= 0 ? P.ncand2[ws] : P.ncand[q];
+        int why = M < 0 ? 4 : -1;                                // >= 0: overflow, CNT_STAT + why counts the reason
         int R = 0, t = 0, off = 0;
-        uint32_t used[WV], s[WV];
-#pragma unroll
-        for (int i = 0; i < WV; ++i) { used[i] = 0u; s[i] = 0u; }
+        uint32_t ul = 0u, sl = 0u;                               // lanes < WV: slots in use / transformed syndrome, word `lane`
         bool finished = false;
-        if (!overflow) {
+        if (why < 0) {
             // ---- reset the row map, then compact rows / slots 0 .. wt-1 for the support of the residual syndrome ----
             {
                 uint4 *rm4 = reinterpret_cast<uint4 *>(rowmap);
@@ -240,7 +283,7 @@ __global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_
                 for (int i = lane; i < m_pad16 / 8; i += 32) rm4[i] = ff;
             }
             __syncwarp();
-            for (int w0 = 0; w0 < mw; w0 += 32) {
+            for (int w0 = 0; w0 < mw && why < 0; w0 += 32) {
                 const int w = w0 + lane;
                 uint32_t word = w < mw ? P.res[(size_t)q * mw + w] : 0u;
                 const int cnt = __popc(word);
@@ -249,7 +292,8 @@ __global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
                 int x = R + inc - cnt;
                 R += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                while (word) {                                   // (the select kernel guarantees wt <= 128 * Q <= rcap)
+                if (R > 128 * Q || R > Tr.rcap) { why = 2; break; }
+                while (word) {
                     const int b = __ffs(word) - 1; word &= word - 1;
                     rowmap[w * 32 + b] = (uint16_t)x;
 #pragma unroll
@@ -265,67 +309,67 @@ __global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_
                     ++x;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < WV; ++i) {
-                const int lo = 32 * i;
+            {
+                const int lo = 32 * lane;
                 const uint32_t msk = R >= lo + 32 ? 0xFFFFFFFFu : (R > lo ? (1u << (R - lo)) - 1u : 0u);
-                used[i] = msk; s[i] = msk;
+                ul = lane < WV ? msk : 0xFFFFFFFFu; sl = lane < WV ? msk : 0u;
             }
             finished = R == 0;
             __syncwarp();
         }
 
         // ---- candidates in reliability order, 32 at a time (ids and signatures prefetched one batch ahead) ----
-        const uint16_t *cand = P.cand + (size_t)q * P.cap;
+        const uint16_t *cand = ws >= 0 ? P.cand2 + (size_t)ws * P.cap2 : P.cand + (size_t)q * P.cap;
         uint32_t idx_cur = 0xFFFFu, idx_nxt = 0xFFFFu;
         uint4 sig_cur = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), sig_nxt = sig_cur;
-        if (!overflow && !finished) {
+        if (why < 0 && !finished) {
             if (lane < M) { idx_cur = cand[lane]; sig_cur = g.colsig[idx_cur]; }
             if (32 + lane < M) idx_nxt = cand[32 + lane];
         }
-        for (int c0 = 0; c0 < M && !overflow && !finished; c0 += 32) {
+        for (int c0 = 0; c0 < M && why < 0 && !finished; c0 += 32) {
             sigbuf[lane] = sig_cur;
             const uint32_t idx_batch = idx_cur;
             __syncwarp();
-            // prefetch the next batch
-            if (c0 + 32 + lane < M) sig_nxt = g.colsig[idx_nxt];
+            if (c0 + 32 + lane < M) sig_nxt = g.colsig[idx_nxt];             // prefetch the next batch
             idx_cur = idx_nxt;
             idx_nxt = (c0 + 64 + lane < M) ? (uint32_t)cand[c0 + 64 + lane] : 0xFFFFu;
             const int cnt = min(32, M - c0);
-            for (int i = 0; i < cnt; ++i) {
+            const uint16_t *sigp = sig16 + k_of_lane;
+#pragma unroll 1
+            for (int i = 0; i < cnt; ++i, sigp += 8) {
                 // ---- v = XOR of the vectors of the candidate's rows (gather layout: k = row slot, w = word) ----
                 uint32_t val = 0u;
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
-                    const int k = ps * KP + k_of_lane;
-                    const uint32_t r = sig16[i * 8 + k];
+                    const uint32_t r = sigp[ps * KP];
                     const bool valid = r != 0xFFFFu;
-                    uint32_t x = valid ? (uint32_t)rowmap[r] : 0xFFFFu;
+                    uint32_t x = valid ? (uint32_t)rowmap[r] : 0u;
                     uint32_t fresh = __ballot_sync(0xFFFFFFFFu, valid && x == 0xFFFFu && w_of_lane == 0);
                     if (fresh) {                                 // rows seen for the first time: next compact row, lowest unused slot
-                        while (fresh) {
+                        do {
                             const int src = __ffs(fresh) - 1; fresh &= fresh - 1;
                             const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, src);
-                            int f = -1;
-#pragma unroll
-                            for (int j = WV - 1; j >= 0; --j) if (used[j] != 0xFFFFFFFFu) f = 32 * j + __ffs(~used[j]) - 1;
-                            if (f < 0 || R >= P.rcap) { overflow = true; break; }
-#pragma unroll
-                            for (int j = 0; j < WV; ++j) if (j == (f >> 5)) used[j] |= 1u << (f & 31);
+                            const uint32_t um = __ballot_sync(0xFFFFFFFFu, ul != 0xFFFFFFFFu);
+                            if (um == 0u) { why = 2; break; }
+                            if (R >= Tr.rcap) { why = 1; break; }
+                            const int wj = __ffs(um) - 1;
+                            const uint32_t uw = __shfl_sync(0xFFFFFFFFu, ul, wj);
+                            const uint32_t fbit = ~uw & (uw + 1u);               // lowest zero bit
+                            if (lane == wj) ul |= fbit;
                             if (lane == 0) rowmap[rr] = (uint16_t)R;
-                            if (lane < WV) Tw[R * WV + lane] = lane == (f >> 5) ? 1u << (f & 31) : 0u;
+                            if (lane < WV) Tw[R * WV + lane] = lane == wj ? fbit : 0u;
                             ++R;
-                        }
-                        if (overflow) break;
+                        } while (fresh);
+                        if (why >= 0) break;
                         __syncwarp();
                         if (valid && x == 0xFFFFu) x = rowmap[r];
                     }
-                    if (valid) val ^= Tw[x * WV + w_of_lane];
+                    if (valid && w_of_lane < WV) val ^= Tw[x * WV + w_of_lane];
                 }
-                if (overflow) break;
+                if (why >= 0) break;
 #pragma unroll
                 for (int o = LV; o < 32; o <<= 1) val ^= __shfl_xor_sync(0xFFFFFFFFu, val, o);
-                const uint32_t nz = __ballot_sync(0xFFFFFFFFu, val != 0u) & ((1u << WV) - 1u);
+                const uint32_t nz = __ballot_sync(0xFFFFFFFFu, val != 0u) & WVMASK;
                 if (nz == 0u) continue;                          // dependent on the pivots so far
                 // ---- pivot: slot b = lowest set bit of v ----
                 const int wsel = __ffs(nz) - 1;
@@ -338,70 +382,86 @@ __global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_
                     v4[qq].z = __shfl_sync(0xFFFFFFFFu, val, 4 * qq + 2); v4[qq].w = __shfl_sync(0xFFFFFFFFu, val, 4 * qq + 3);
                 }
                 const int nwr = (R + 31) >> 5;
-                if (off + nwr > P.rec_cap || t >= P.rcap) { overflow = true; break; }
-                // every vector with bit b: ^= v (clears bit b: the slot is free again); the ballots are the frozen row
-                for (int blk = 0; blk < nwr; ++blk) {
-                    const int x = blk * 32 + lane;
-                    bool has = false;
-                    if (x < R) {
-                        if constexpr (Q == 1) {
-                            uint4 col = T4[x];
-                            has = (u4_word(col, wsel) & bmask) != 0u;
-                            if (has) { col.x ^= v4[0].x; col.y ^= v4[0].y; col.z ^= v4[0].z; col.w ^= v4[0].w; T4[x] = col; }
-                        } else {
-                            has = (Tw[x * WV + wsel] & bmask) != 0u;
-                            if (has) {
+                if (off + nwr > Tr.rec_cap || t >= Tr.rcap) { why = 3; break; }
+                // every vector with bit b: ^= v (clears bit b: the slot is free again); the ballots are the frozen row.
+                // Branch-free: every lane loads, masks and stores its row (rows >= R lie inside the T buffer and are dead).
+                uint32_t myflags = 0u;
+                uint32_t bm[WV];
 #pragma unroll
-                                for (int qq = 0; qq < Q; ++qq) {
-                                    uint4 col = T4[x * Q + qq];
-                                    col.x ^= v4[qq].x; col.y ^= v4[qq].y; col.z ^= v4[qq].z; col.w ^= v4[qq].w;
-                                    T4[x * Q + qq] = col;
-                                }
-                            }
-                        }
+                for (int j = 0; j < WV; ++j) bm[j] = j == wsel ? bmask : 0u;
+                uint4 *tp = T4 + (size_t)lane * Q;
+                const int nblk = min(nwr, Tr.rcap >> 5);
+                auto scan_block = [&](int blk) -> uint32_t {
+                    uint4 col[Q];
+                    uint32_t hit = 0u;
+#pragma unroll
+                    for (int qq = 0; qq < Q; ++qq) {
+                        col[qq] = tp[qq];
+                        hit |= (col[qq].x & bm[4 * qq]) | (col[qq].y & bm[4 * qq + 1]) | (col[qq].z & bm[4 * qq + 2]) | (col[qq].w & bm[4 * qq + 3]);
                     }
-                    const uint32_t flags = __ballot_sync(0xFFFFFFFFu, has);
+                    const bool has = hit != 0u && blk * 32 + lane < R;
+                    const uint32_t mk = has ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+                    for (int qq = 0; qq < Q; ++qq) {
+                        col[qq].x ^= v4[qq].x & mk; col[qq].y ^= v4[qq].y & mk; col[qq].z ^= v4[qq].z & mk; col[qq].w ^= v4[qq].w & mk;
+                        tp[qq] = col[qq];
+                    }
+                    tp += 32 * Q;
+                    return __ballot_sync(0xFFFFFFFFu, has);
+                };
+                const int nb1 = min(nblk, 32);
+#pragma unroll 2
+                for (int blk = 0; blk < nb1; ++blk) { const uint32_t flags = scan_block(blk); if (blk == lane) myflags = flags; }
+                for (int blk = 32; blk < nblk; ++blk) {                      // (more than 1024 touched rows)
+                    const uint32_t flags = scan_block(blk);
                     if (lane == 0) rec[off + blk] = flags;
                 }
-                uint32_t sw = 0u;
-#pragma unroll
-                for (int j = 0; j < WV; ++j) if (j == wsel) sw = s[j];
-                const uint32_t sigma = (sw & bmask) ? 1u : 0u;
-                uint32_t any = 0u;
-#pragma unroll
-                for (int j = 0; j < WV; ++j) {
-                    if (sigma) s[j] ^= u4_word(v4[j >> 2], j & 3);
-                    if (j == wsel) used[j] &= ~bmask;
-                    any |= s[j];
-                }
+                if (lane < nwr) rec[off + lane] = myflags;
+                const uint32_t sigma = __ballot_sync(0xFFFFFFFFu, lane == wsel && (sl & bmask) != 0u) ? 1u : 0u;
+                if (sigma && lane < WV) sl ^= val;
+                if (lane == wsel) ul &= ~bmask;
                 const uint32_t col_id = __shfl_sync(0xFFFFFFFFu, idx_batch, i);
                 if (lane == 0) meta[t] = col_id | (sigma << 16) | ((uint32_t)nwr << 17);
                 off += nwr; ++t;
                 __syncwarp();
-                if (any == 0u) { finished = true; break; }
+                if (__ballot_sync(0xFFFFFFFFu, lane < WV && sl != 0u) == 0u) { finished = true; break; }
             }
             sig_cur = sig_nxt;
             __syncwarp();
         }
-        if (!finished) overflow = true;                          // window exhausted (or nothing materialised)
-        if (overflow) {
-            if (lane == 0) { const int o = atomicAdd(&P.counters[2], 1); P.ovf_idx[o] = shot; }
+        if (why < 0 && !finished) why = 0;                       // window exhausted
+        if (why >= 0) {
+            if (lane == 0) {
+                const int o = atomicAdd(&P.counters[Tr.out_counter], 1);
+                Tr.out_list[o] = Tr.out_shots ? shot : q;
+                // whatever made the side leave this tier, it is a heavy one: the next tier gets all columns in order
+                if (why != 4 && Tr.win_list && ws < 0) Tr.win_list[atomicAdd(&P.counters[CNT_WIN_A], 1)] = q;
+                atomicAdd(&P.counters[(Tr.out_shots ? CNT_STAT_B : CNT_STAT) + why], 1);
+            }
             continue;
         }
-        // ---- back substitution over the frozen rows, last pivot first ----
+        // ---- back substitution over the frozen rows, last pivot first (records prefetched one pivot ahead) ----
         for (int w = lane; w < (R + 31) >> 5; w += 32) ybits[w] = 0u;
         __syncwarp();
         uint32_t *hard_rw = P.a.hard_bits + (size_t)shot * g.nw;
-        uint32_t mt_nxt = t > 0 ? ldcg_u32(&meta[t - 1]) : 0u;
+        uint32_t mtA = t > 0 ? ldcg_u32(&meta[t - 1]) : 0u, mtB = t > 1 ? ldcg_u32(&meta[t - 2]) : 0u;
+        int offA = off - (int)(mtA >> 17);
+        uint32_t recA = (t > 0 && lane < (int)(mtA >> 17)) ? ldcg_u32(&rec[offA + lane]) : 0u;
+        uint32_t sigA = (t > 0 && lane < 8) ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
         for (int tt = t - 1; tt >= 0; --tt) {
-            const uint32_t mt = mt_nxt;
-            if (tt > 0) mt_nxt = ldcg_u32(&meta[tt - 1]);
+            const uint32_t mt = mtA, recw = recA, r = sigA;
+            const int offc = offA;
             const int nwr = (int)(mt >> 17), col = (int)(mt & 0xFFFFu);
-            off -= nwr;
-            // signature of the column (needed only when e_t = 1, but loaded ahead of the parity to hide its latency)
-            const uint32_t r = lane < 8 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(g.colsig) + (size_t)col * 8 + lane) : 0xFFFFu;
-            uint32_t par = 0u;
-            for (int w = lane; w < nwr; w += 32) par ^= (uint32_t)__popc(ldcg_u32(&rec[off + w]) & ybits[w]);
+            mtA = mtB;
+            mtB = tt >= 2 ? ldcg_u32(&meta[tt - 2]) : 0u;
+            if (tt >= 1) {
+                const int nwa = (int)(mtA >> 17);
+                offA = offc - nwa;
+                recA = lane < nwa ? ldcg_u32(&rec[offA + lane]) : 0u;
+                sigA = lane < 8 ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
+            }
+            uint32_t par = lane < nwr ? (uint32_t)__popc(recw & ybits[lane]) : 0u;
+            for (int w = 32 + lane; w < nwr; w += 32) par ^= (uint32_t)__popc(ldcg_u32(&rec[offc + w]) & ybits[w]);
             par = __reduce_xor_sync(0xFFFFFFFFu, par) & 1u;
             if ((((mt >> 16) & 1u) ^ par) != 0u) {
                 if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
@@ -415,38 +475,66 @@ __global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_
 }
 
 // ---- launcher ---------------------------------------------------------------------------------------------------
-struct FreePlan { int Q, rcap, cap, sel_min, rec_cap, ctas_per_sm, warps; size_t smem_sel, smem_free; };
+struct FreeTierPlan { int Q, rcap, rec_cap, warps, ctas_per_sm; size_t smem; };
+struct FreePlan { int cap, cap2, cap_per_wt, max_wt; size_t smem_sel, smem_sel2; FreeTierPlan A, B; };
+
+static bool tier_plan(const qb_decoder *dec, int Q, int rcap, int max_warps, FreeTierPlan &tp)
+{
+    const GraphDev &g = dec->g;
+    tp.Q = Q;
+    tp.rcap = std::max(128 * Q, std::min(rcap, (g.m + 31) & ~31)) & ~31;
+    tp.rec_cap = tp.rcap * std::max(4, tp.rcap * 3 / 128);                  // 3/4 of rcap * rcap / 32 (the records are triangular)
+    const size_t per_warp = free_per_warp_bytes(g.m, tp.rcap, Q);
+    const size_t limit = (size_t)dec->max_smem_optin;
+    if (per_warp + 1024 > limit) return false;
+    tp.warps = (int)std::min<size_t>(max_warps, (limit - 1024) / per_warp);
+    tp.smem = per_warp * tp.warps;
+    tp.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (limit + 1024) / (tp.smem + 1024)));
+    return true;
+}
 
 static bool free_plan(const qb_decoder *dec, FreePlan &pl)
 {
     const GraphDev &g = dec->g;
     if (!g.colsig || g.n > 65535 || g.m > 65535 || g.m <= 0 || g.n <= 0) return false;
     if (getenv("QLDPC_B200_OSD_FULLWIDTH")) return false;
-    pl.Q = g.m <= 1536 ? 1 : 2;
-    pl.rcap = g.m <= 1536 ? 512 : 2048;
-    if (const char *e = getenv("QLDPC_B200_OSD_RCAP")) { const int v = atoi(e); if (v >= 128 && v <= 4096) pl.rcap = v & ~31; }
-    pl.rcap = std::min(pl.rcap, (g.m + 31) & ~31);
-    pl.cap = g.m <= 1536 ? 1024 : 8192;
+    const bool big = g.m > 1536;
+    int rcapA = big ? 2048 : 512, rcapB = big ? 3072 : 1024;
+    if (const char *e = getenv("QLDPC_B200_OSD_RCAP")) { const int v = atoi(e); if (v >= 128 && v <= 4096) { rcapA = v; rcapB = 2 * v; } }
+    pl.cap = big ? 8192 : 2048;
     if (const char *e = getenv("QLDPC_B200_OSD_CAP")) { const int v = atoi(e); if (v >= 64 && v <= 16384) pl.cap = v & ~31; }
-    pl.cap = std::min(pl.cap, (g.n + 31) & ~31);
-    pl.sel_min = std::max(32, pl.cap - pl.cap / 8);
-    pl.rec_cap = pl.rcap * std::max(4, pl.rcap * 3 / 128);                  // 3/4 of rcap * rcap / 32 (the records are triangular)
-    const int m_pad16 = (g.m + 7) & ~7;
-    const size_t per_warp = ((size_t)m_pad16 * 2 + (size_t)pl.rcap * 16 * pl.Q + 512 + 64 + (size_t)(pl.rcap / 32) * 4 + 15) & ~(size_t)15;
-    const size_t limit = (size_t)dec->max_smem_optin;
-    pl.warps = (int)std::min<size_t>(FREE_WARPS, (limit - 1024) / per_warp);
-    if (pl.warps < 1) return false;
-    pl.smem_free = per_warp * pl.warps;
-    pl.smem_sel = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap * (4 + 2 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
-    if (pl.smem_free + 1024 > limit || pl.smem_sel + 1024 > limit) return false;
-    pl.ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (limit + 1024) / (pl.smem_free + 1024)));
-    return true;
+    pl.cap = std::max(32, std::min(pl.cap, (g.n + 31) & ~31));
+    pl.cap_per_wt = 28;
+    if (!tier_plan(dec, big ? 2 : 1, rcapA, FREE_WARPS, pl.A)) return false;
+    if (!tier_plan(dec, big ? 3 : 2, rcapB, FREE_WARPS, pl.B)) return false;
+    pl.max_wt = 128 * pl.B.Q;
+    pl.cap2 = (g.n + 31) & ~31;                                              // second pass: all columns
+    pl.smem_sel = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap * (4 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
+    pl.smem_sel2 = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap2 * (4 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
+    return pl.smem_sel + 1024 <= (size_t)dec->max_smem_optin && pl.smem_sel2 + 1024 <= (size_t)dec->max_smem_optin;
 }
 
 bool osd_free_applicable(const qb_decoder *dec) { FreePlan pl; return free_plan(dec, pl); }
 
-// Selection + free-row elimination for the queue of `a`; sides that do not fit end in the overflow queue
-// (*ovf_count_d / *ovf_idx_d, device pointers valid until the decoder's next OSD launch).
+template <int Q>
+static int launch_tier(const OsdFreeArgs &P, const OsdFreeTier &T, const FreeTierPlan &tp, int grid, cudaStream_t st)
+{
+    QB_CUDA(cudaFuncSetAttribute(osd_free_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+    osd_free_kernel<Q><<<grid, tp.warps * 32, tp.smem, st>>>(P, T);
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+static int launch_tier_q(const OsdFreeArgs &P, const OsdFreeTier &T, const FreeTierPlan &tp, int grid, cudaStream_t st)
+{
+    switch (tp.Q) {
+        case 1: return launch_tier<1>(P, T, tp, grid, st);
+        case 2: return launch_tier<2>(P, T, tp, grid, st);
+        default: return launch_tier<3>(P, T, tp, grid, st);
+    }
+}
+
+// Selection + two tiers of free-row elimination for the queue of `a`; what fits neither tier ends in the overflow queue
+// (*ovf_count_d / *ovf_idx_d: shot indices; device pointers valid until the decoder's next OSD launch).
 int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d, int32_t **ovf_idx_d, cudaStream_t st)
 {
     FreePlan pl;
@@ -454,37 +542,79 @@ int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d,
     const GraphDev &g = dec->g;
     OsdFreeArgs P{};
     P.g = g; P.a = a; P.F = a.F;
-    P.cap = pl.cap; P.sel_min = pl.sel_min; P.rcap = pl.rcap; P.fw_bits = 128 * pl.Q; P.rec_cap = pl.rec_cap;
-    const int grid_free = std::max(1, std::min(ceil_div(a.F, pl.warps), dec->sm_count * pl.ctas_per_sm));
+    P.cap = pl.cap; P.cap_per_wt = pl.cap_per_wt; P.max_wt = pl.max_wt;
+    const int gridA = std::max(1, std::min(ceil_div(a.F, pl.A.warps), dec->sm_count * pl.A.ctas_per_sm));
+    const int gridB = std::max(1, std::min(ceil_div(a.F, pl.B.warps), dec->sm_count * pl.B.ctas_per_sm));
     const int sel_ctas = (int)std::max<size_t>(1, std::min<size_t>(2048 / SELF_THREADS, ((size_t)dec->max_smem_optin + 1024) / (pl.smem_sel + 1024)));
     const int grid_sel = std::max(1, std::min(a.F, dec->sm_count * sel_ctas));
-    const size_t slots = (size_t)grid_free * pl.warps;
+    const size_t slotsA = (size_t)gridA * pl.A.warps, slotsB = (size_t)gridB * pl.B.warps;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t F = (size_t)a.F;
-    const size_t need = 256 + al(F * pl.cap * 2) + al(F * 4) + al(F * g.mw * 4) + al(slots * pl.rec_cap * 4) + al(slots * pl.rcap * 4) + al(F * 4);
+    const size_t F2 = std::max<size_t>(64, F / 16);                             // sides the second selection pass has buffers for
+    const size_t need = 256 + al(F * pl.cap * 2) + al(F * 4) + al(F * g.mw * 4) + al(slotsA * pl.A.rec_cap * 4) + al(slotsA * pl.A.rcap * 4) +
+                        al(slotsB * pl.B.rec_cap * 4) + al(slotsB * pl.B.rcap * 4) + 4 * al(F * 4) + al(F2 * pl.cap2 * 2) + al(F2 * 4);
+    const bool grown = dec->ovf.cap < need;
     if (int rc = dec->ovf.ensure(need)) return rc;
     unsigned char *p = dec->ovf.as<unsigned char>();
+    if (grown) QB_CUDA(cudaMemsetAsync(p, 0, 256, st));
     P.counters = reinterpret_cast<int32_t *>(p); p += 256;
     P.cand = reinterpret_cast<uint16_t *>(p); p += al(F * pl.cap * 2);
     P.ncand = reinterpret_cast<int32_t *>(p); p += al(F * 4);
     P.res = reinterpret_cast<uint32_t *>(p); p += al(F * g.mw * 4);
-    P.rec = reinterpret_cast<uint32_t *>(p); p += al(slots * pl.rec_cap * 4);
-    P.meta = reinterpret_cast<uint32_t *>(p); p += al(slots * pl.rcap * 4);
-    P.ovf_idx = reinterpret_cast<int32_t *>(p);
-    QB_CUDA(cudaMemsetAsync(P.counters, 0, 16, st));
-    QB_CUDA(cudaFuncSetAttribute(osd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_sel));
+    OsdFreeTier TA{}, TB{};
+    TA.rcap = pl.A.rcap; TA.rec_cap = pl.A.rec_cap; TB.rcap = pl.B.rcap; TB.rec_cap = pl.B.rec_cap;
+    TA.rec = reinterpret_cast<uint32_t *>(p); p += al(slotsA * pl.A.rec_cap * 4);
+    TA.meta = reinterpret_cast<uint32_t *>(p); p += al(slotsA * pl.A.rcap * 4);
+    TB.rec = reinterpret_cast<uint32_t *>(p); p += al(slotsB * pl.B.rec_cap * 4);
+    TB.meta = reinterpret_cast<uint32_t *>(p); p += al(slotsB * pl.B.rcap * 4);
+    int32_t *listA = reinterpret_cast<int32_t *>(p); p += al(F * 4);
+    int32_t *listB = reinterpret_cast<int32_t *>(p); p += al(F * 4);
+    int32_t *listW = reinterpret_cast<int32_t *>(p); p += al(F * 4);
+    P.win_slot = reinterpret_cast<int32_t *>(p); p += al(F * 4);
+    uint16_t *cand2 = reinterpret_cast<uint16_t *>(p); p += al(F2 * pl.cap2 * 2);
+    int32_t *ncand2 = reinterpret_cast<int32_t *>(p);
+    P.win_list = listW; P.cand2 = cand2; P.ncand2 = ncand2; P.cap2 = pl.cap2; P.sel_max = (int)F2;
+    TA.queue_counter = CNT_A; TA.in_count = nullptr; TA.in_q = nullptr; TA.out_counter = CNT_OVF_A; TA.out_list = listA; TA.out_shots = 0; TA.win_list = listW;
+    TB.queue_counter = CNT_B; TB.in_count = P.counters + CNT_OVF_A; TB.in_q = listA; TB.out_counter = CNT_OVF_B; TB.out_list = listB; TB.out_shots = 1; TB.win_list = nullptr;
+    static const bool dbg = getenv("QLDPC_B200_DEBUG_SYNC") != nullptr;
+    // the statistics words accumulate over launches (qb_debug_osd_free_stats reads and clears them)
+    QB_CUDA(cudaMemsetAsync(P.counters, 0, CNT_STAT * sizeof(int32_t), st));
+    QB_CUDA(cudaMemsetAsync(P.win_slot, 0xFF, F * sizeof(int32_t), st));
+    QB_CUDA(cudaFuncSetAttribute(osd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(pl.smem_sel, pl.smem_sel2)));
+    P.sel_count = nullptr; P.sel_q = nullptr; P.sel_counter = CNT_SEL;
     osd_select_kernel<<<grid_sel, SELF_THREADS, pl.smem_sel, st>>>(P);
     QB_CUDA(cudaGetLastError());
-    if (pl.Q == 1) {
-        QB_CUDA(cudaFuncSetAttribute(osd_free_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_free));
-        osd_free_kernel<1><<<grid_free, pl.warps * 32, pl.smem_free, st>>>(P);
-    } else {
-        QB_CUDA(cudaFuncSetAttribute(osd_free_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_free));
-        osd_free_kernel<2><<<grid_free, pl.warps * 32, pl.smem_free, st>>>(P);
+    if (dbg) QB_CUDA(cudaStreamSynchronize(st));
+    if (int rc = launch_tier_q(P, TA, pl.A, gridA, st)) return rc;
+    if (dbg) QB_CUDA(cudaStreamSynchronize(st));
+    {   // sides that ran out of candidates get the full window before tier B looks at them
+        OsdFreeArgs P2 = P;
+        P2.sel_count = P.counters + CNT_WIN_A; P2.sel_q = listW; P2.sel_counter = CNT_SEL2;
+        P2.cand = cand2; P2.ncand = ncand2; P2.cap = pl.cap2;
+        QB_CUDA(cudaFuncSetAttribute(osd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(pl.smem_sel, pl.smem_sel2)));
+        osd_select_kernel<<<(int)std::min<size_t>(F2, (size_t)dec->sm_count * 2), SELF_THREADS, pl.smem_sel2, st>>>(P2);
+        QB_CUDA(cudaGetLastError());
+        if (dbg) QB_CUDA(cudaStreamSynchronize(st));
     }
-    QB_CUDA(cudaGetLastError());
-    *ovf_count_d = P.counters + 2;
-    *ovf_idx_d = P.ovf_idx;
+    if (int rc = launch_tier_q(P, TB, pl.B, gridB, st)) return rc;
+    if (dbg) QB_CUDA(cudaStreamSynchronize(st));
+    *ovf_count_d = P.counters + CNT_OVF_B;
+    *ovf_idx_d = listB;
+    return QB_OK;
+}
+
+// statistics of the free-row path since the last call: sides that left tier A (out[0..4]) / tier B (out[5..9], these go to
+// the full-width kernel) because of {window exhausted, touched rows, free slots, record buffer, not materialised}
+int osd_free_stats(qb_decoder *dec, int32_t *out10)
+{
+    for (int i = 0; i < 10; ++i) out10[i] = 0;
+    if (!dec->ovf.ptr) return QB_OK;
+    QB_CUDA(cudaDeviceSynchronize());
+    int32_t *c = dec->ovf.as<int32_t>() + CNT_STAT;
+    int32_t h[16];
+    QB_CUDA(cudaMemcpy(h, c, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemset(c, 0, 16 * sizeof(int32_t)));
+    for (int i = 0; i < 5; ++i) { out10[i] = h[i]; out10[5 + i] = h[8 + i]; }
     return QB_OK;
 }
 
