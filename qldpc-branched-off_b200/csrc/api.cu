@@ -1,5 +1,7 @@
 // C ABI of libqldpc_b200.so: handles, host staging and the fused per-shot pipeline.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -673,25 +675,37 @@ int qb_sample_syndromes(qb_sampler *s, uint64_t seed, uint64_t first_shot, int32
 }  // extern "C"
 
 // ---- pipeline -------------------------------------------------------------------------------------
-struct qb_pipeline {
-    qb_sampler *s = nullptr;
-    qb_decoder *dz = nullptr, *dx = nullptr;
-    int max_batch = 0;
-    cudaStream_t st = nullptr;        // stream all pipeline work is issued on
-    cudaStream_t own_st = nullptr;    // the pipeline's own stream (default)
-    cudaStream_t side_st = nullptr;   // second stream: the X side's OSD-0 runs beside the Z side's and fills its tail
+// Per-batch buffers.  A pipeline owns two of them: consecutive batches of one qb_pipeline_run call alternate, each on
+// its own stream, so that the sampling and min-sum of batch i+1 fill the SMs the OSD-0 tail of batch i no longer uses.
+struct qb_workspace {
+    cudaStream_t st = nullptr;        // stream the batch is issued on (workspace 0: the pipeline's / the caller's stream)
+    cudaStream_t own_st = nullptr;
+    cudaStream_t side_st = nullptr;   // the X side's OSD-0 runs beside the Z side's and fills its tail
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_ms_done = nullptr, ev_osd_done = nullptr;   // min-sum / OSD of the batch in this workspace finished
     uint32_t *synZ = nullptr, *synX = nullptr, *trueZ = nullptr, *trueX = nullptr, *hardZ = nullptr, *hardX = nullptr;
     uint8_t *convZ = nullptr, *convX = nullptr, *flags = nullptr;
     int32_t *itZ = nullptr, *itX = nullptr, *failZ = nullptr, *failX = nullptr, *nfail = nullptr;   // nfail[2]
     int32_t *fwZ = nullptr, *fwX = nullptr, *sortZ = nullptr, *sortX = nullptr;   // failure weights / weight-sorted queues
     float *postZ = nullptr, *postX = nullptr;
+    int32_t *osdinfoZ = nullptr, *osdinfoX = nullptr;   // per shot: pivots used | OSD path << 16 (detail mode only)
+    bool ms_pending = false, osd_pending = false;        // the events above have been recorded in the current run
+};
+
+struct qb_pipeline {
+    qb_sampler *s = nullptr;
+    qb_decoder *dz = nullptr, *dx = nullptr;
+    int max_batch = 0;
+    cudaStream_t st = nullptr;        // stream of workspace 0 (own or the caller's)
+    cudaStream_t own_st = nullptr;
+    qb_workspace ws[2];
+    int n_ws = 2;
+    cudaEvent_t ev_begin = nullptr, ev_tail = nullptr;   // run start (second stream waits for it) / second stream drained
     int64_t *counts = nullptr;   // device [8]
     int32_t *ev_ptr = nullptr; uint32_t *events = nullptr; size_t ev_cap = 0;
     int8_t *syn8 = nullptr;      // staging for decode_host
-    int32_t *osdinfoZ = nullptr, *osdinfoX = nullptr;   // per shot: pivots used | OSD path << 16 (detail mode only)
     int detail = 0;              // qb_pipeline_enable_detail
-    int last_B = 0;              // shots of the last batch (what qb_pipeline_last_batch_detail may read)
+    int last_B = 0, last_ws = 0; // shots / workspace of the last batch (what qb_pipeline_last_batch_detail may read)
     std::vector<void *> owned;
     std::vector<cudaEvent_t> evs;
     qb_pipeline_stats stats{};
@@ -729,56 +743,75 @@ static int prep_alpha(qb_pipeline *p, const qb_decode_config *cfg)
     return upload_alpha(p->dx, cfg->max_iter, cfg->alpha_mode, cfg->alpha_x, sx.data(), cfg->alpha_len_x, p->st);
 }
 
-// decode + logical check of one batch whose syndromes / true masks already sit in p->syn*, p->true*
-static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int batch_no)
+// start of a run: counters cleared, alpha tables uploaded on workspace 0's stream; the second stream starts after that
+static int begin_run(qb_pipeline *p, const qb_decode_config *cfg)
 {
-    cudaStream_t st = p->st;
+    p->stats = qb_pipeline_stats{};
+    p->ws[0].st = p->st;
+    for (int w = 0; w < 2; ++w) { p->ws[w].ms_pending = false; p->ws[w].osd_pending = false; }
+    if (int rc = prep_alpha(p, cfg)) return rc;
+    QB_CUDA(cudaMemsetAsync(p->counts, 0, 8 * sizeof(int64_t), p->st));
+    QB_CUDA(cudaEventRecord(p->ev_begin, p->st));
+    QB_CUDA(cudaStreamWaitEvent(p->ws[1].st, p->ev_begin, 0));
+    return QB_OK;
+}
+
+// decode + logical check of one batch whose syndromes / true masks already sit in the workspace.  The decoders' own
+// scratch (shot queue of the persistent min-sum kernel, OSD work areas) is shared by the two workspaces: min-sum of this
+// batch waits for the other workspace's min-sum, OSD for its OSD -- which also is the order that keeps the SMs busy.
+static int decode_batch(qb_pipeline *p, qb_workspace &W, qb_workspace &other, int B, const qb_decode_config *cfg, int batch_no)
+{
+    cudaStream_t st = W.st;
     const bool timed = batch_no < MAX_TIMED_BATCHES;
     cudaEvent_t *ev = timed ? &p->evs[(size_t)batch_no * EV_PER_BATCH] : nullptr;
-    p->last_B = B;
-    QB_CUDA(cudaMemsetAsync(p->nfail, 0, 2 * sizeof(int32_t), st));
+    p->last_B = B; p->last_ws = (int)(&W - p->ws);
+    QB_CUDA(cudaMemsetAsync(W.nfail, 0, 2 * sizeof(int32_t), st));
     if (p->detail) {
-        QB_CUDA(cudaMemsetAsync(p->osdinfoZ, 0, (size_t)B * sizeof(int32_t), st));
-        QB_CUDA(cudaMemsetAsync(p->osdinfoX, 0, (size_t)B * sizeof(int32_t), st));
+        QB_CUDA(cudaMemsetAsync(W.osdinfoZ, 0, (size_t)B * sizeof(int32_t), st));
+        QB_CUDA(cudaMemsetAsync(W.osdinfoX, 0, (size_t)B * sizeof(int32_t), st));
     }
+    if (other.ms_pending) QB_CUDA(cudaStreamWaitEvent(st, other.ev_ms_done, 0));
     for (int side = 0; side < 2; ++side) {
         qb_decoder *d = side ? p->dx : p->dz;
         MinsumLaunch a{};
-        a.syn_bits = side ? p->synX : p->synZ; a.B = B; a.max_iter = cfg->max_iter; a.alpha_d = d->d_alpha;
+        a.syn_bits = side ? W.synX : W.synZ; a.B = B; a.max_iter = cfg->max_iter; a.alpha_d = d->d_alpha;
         a.damping = 1.0f; a.clip = cfg->clip_llr; a.dense_variant = 0;
-        a.hard_bits = side ? p->hardX : p->hardZ; a.converged = side ? p->convX : p->convZ;
-        a.final_iter = side ? p->itX : p->itZ; a.post = side ? p->postX : p->postZ; a.post_failed_only = 1;
-        a.fail_count = p->nfail + side; a.fail_idx = side ? p->failX : p->failZ; a.fail_wt = side ? p->fwX : p->fwZ;
+        a.hard_bits = side ? W.hardX : W.hardZ; a.converged = side ? W.convX : W.convZ;
+        a.final_iter = side ? W.itX : W.itZ; a.post = side ? W.postX : W.postZ; a.post_failed_only = 1;
+        a.fail_count = W.nfail + side; a.fail_idx = side ? W.failX : W.failZ; a.fail_wt = side ? W.fwX : W.fwZ;
         if (int rc = launch_minsum(d, a, st)) return rc;
         p->stats.kernel_launches++;
     }
+    QB_CUDA(cudaEventRecord(W.ev_ms_done, st)); W.ms_pending = true;
     if (timed) QB_CUDA(cudaEventRecord(ev[EV_MINSUM], st));
     if (cfg->use_osd) {
-        // The two sides are independent (own decoders, own workspaces): the X side is issued on a second stream, so
+        if (other.osd_pending) QB_CUDA(cudaStreamWaitEvent(st, other.ev_osd_done, 0));
+        // The two sides are independent (own decoders, own work areas): the X side is issued on a second stream, so
         // that its CTAs take the SMs the Z launch frees while its last, longest eliminations finish.
-        const bool fork = p->dz != p->dx && p->side_st != nullptr;
-        if (fork) { QB_CUDA(cudaEventRecord(p->ev_fork, st)); QB_CUDA(cudaStreamWaitEvent(p->side_st, p->ev_fork, 0)); }
+        const bool fork = p->dz != p->dx && W.side_st != nullptr;
+        if (fork) { QB_CUDA(cudaEventRecord(W.ev_fork, st)); QB_CUDA(cudaStreamWaitEvent(W.side_st, W.ev_fork, 0)); }
         for (int side = 0; side < 2; ++side) {
             qb_decoder *d = side ? p->dx : p->dz;
-            cudaStream_t ss = (fork && side) ? p->side_st : st;
-            if (int rc = launch_sort_failures(side ? p->failX : p->failZ, side ? p->fwX : p->fwZ, p->nfail + side,
-                                              side ? p->sortX : p->sortZ, ss)) return rc;
+            cudaStream_t ss = (fork && side) ? W.side_st : st;
+            if (int rc = launch_sort_failures(side ? W.failX : W.failZ, side ? W.fwX : W.fwZ, W.nfail + side,
+                                              side ? W.sortX : W.sortZ, ss)) return rc;
             p->stats.kernel_launches++;
             OsdLaunch a{};
-            a.syn_bits = side ? p->synX : p->synZ; a.hard_bits = side ? p->hardX : p->hardZ;
-            a.post = side ? p->postX : p->postZ; a.fail_idx = side ? p->sortX : p->sortZ;
-            a.F = B; a.n_fail_d = p->nfail + side;
-            if (p->detail) { a.rank_out = side ? p->osdinfoX : p->osdinfoZ; a.rank_tag = 2 << 16; }
+            a.syn_bits = side ? W.synX : W.synZ; a.hard_bits = side ? W.hardX : W.hardZ;
+            a.post = side ? W.postX : W.postZ; a.fail_idx = side ? W.sortX : W.sortZ;
+            a.F = B; a.n_fail_d = W.nfail + side;
+            if (p->detail) { a.rank_out = side ? W.osdinfoX : W.osdinfoZ; a.rank_tag = 2 << 16; }
             if (int rc = launch_osd0(d, a, ss)) return rc;
-            p->stats.kernel_launches++;
+            p->stats.kernel_launches += osd_launches_per_call(d);
         }
-        if (fork) { QB_CUDA(cudaEventRecord(p->ev_join, p->side_st)); QB_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0)); }
+        if (fork) { QB_CUDA(cudaEventRecord(W.ev_join, W.side_st)); QB_CUDA(cudaStreamWaitEvent(st, W.ev_join, 0)); }
+        QB_CUDA(cudaEventRecord(W.ev_osd_done, st)); W.osd_pending = true;
     }
     if (timed) QB_CUDA(cudaEventRecord(ev[EV_OSD], st));
-    if (int rc = launch_logical_check(p->dz, p->hardZ, p->trueZ, B, p->flags, 0, p->counts, 0, st)) return rc;
-    if (int rc = launch_logical_check(p->dx, p->hardX, p->trueX, B, p->flags, 1, p->counts, 1, st)) return rc;
+    if (int rc = launch_logical_check(p->dz, W.hardZ, W.trueZ, B, W.flags, 0, p->counts, 0, st)) return rc;
+    if (int rc = launch_logical_check(p->dx, W.hardX, W.trueX, B, W.flags, 1, p->counts, 1, st)) return rc;
     batch_counts_kernel<<<std::max(1, std::min(ceil_div(B, 256), 256)), 256, 0, st>>>(
-        p->flags, p->convZ, p->convX, p->itZ, p->itX, B, reinterpret_cast<unsigned long long *>(p->counts));
+        W.flags, W.convZ, W.convX, W.itZ, W.itX, B, reinterpret_cast<unsigned long long *>(p->counts));
     QB_CUDA(cudaGetLastError());
     p->stats.kernel_launches += 3;
     if (timed) QB_CUDA(cudaEventRecord(ev[EV_END], st));
@@ -787,9 +820,14 @@ static int decode_batch(qb_pipeline *p, int B, const qb_decode_config *cfg, int 
 
 static int finish_run(qb_pipeline *p, int n_batches, int64_t *counts_h)
 {
+    if (n_batches > 1) {      // the second stream's batches complete before the counters are read on workspace 0's stream
+        QB_CUDA(cudaEventRecord(p->ev_tail, p->ws[1].st));
+        QB_CUDA(cudaStreamWaitEvent(p->st, p->ev_tail, 0));
+    }
     QB_CUDA(cudaMemcpyAsync(counts_h, p->counts, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, p->st));
     QB_CUDA(cudaStreamSynchronize(p->st));
     const int nb = std::min(n_batches, MAX_TIMED_BATCHES);
+    float t_end = 0.f;
     for (int b = 0; b < nb; ++b) {
         cudaEvent_t *ev = &p->evs[(size_t)b * EV_PER_BATCH];
         float t;
@@ -797,12 +835,16 @@ static int finish_run(qb_pipeline *p, int n_batches, int64_t *counts_h)
         QB_CUDA(cudaEventElapsedTime(&t, ev[EV_SAMPLED], ev[EV_MINSUM])); p->stats.ms_minsum += t;
         QB_CUDA(cudaEventElapsedTime(&t, ev[EV_MINSUM], ev[EV_OSD])); p->stats.ms_osd += t;
         QB_CUDA(cudaEventElapsedTime(&t, ev[EV_OSD], ev[EV_END])); p->stats.ms_logical += t;
+        QB_CUDA(cudaEventElapsedTime(&t, p->evs[EV_START], ev[EV_END])); t_end = std::max(t_end, t);
     }
-    if (nb > 0) {
-        float t;
-        QB_CUDA(cudaEventElapsedTime(&t, p->evs[EV_START], p->evs[(size_t)(nb - 1) * EV_PER_BATCH + EV_END]));
-        p->stats.ms_total = t;
-    }
+    if (getenv("QLDPC_B200_TIMELINE"))
+        for (int b = 0; b < nb; ++b) {
+            cudaEvent_t *ev = &p->evs[(size_t)b * EV_PER_BATCH];
+            float t[EV_PER_BATCH];
+            for (int k = 0; k < EV_PER_BATCH; ++k) cudaEventElapsedTime(&t[k], p->evs[EV_START], ev[k]);
+            fprintf(stderr, "batch %d ws %d: start %.2f sampled %.2f minsum %.2f osd %.2f end %.2f ms\n", b, b & 1, t[0], t[1], t[2], t[3], t[4]);
+        }
+    p->stats.ms_total = t_end;           // first batch's start to the last completion (stage times overlap across batches)
     p->stats.edge_messages = counts_h[6] * (int64_t)p->dz->g.nnz + counts_h[7] * (int64_t)p->dx->g.nnz;
     p->stats.osd_sides = counts_h[4] + counts_h[5];
     return QB_OK;
@@ -826,18 +868,38 @@ int qb_pipeline_create(qb_sampler *s, qb_decoder *decZ, qb_decoder *decX, int32_
     const size_t B = (size_t)max_batch;
     const GraphDev &gz = decZ->g, &gx = decX->g;
     int rc = QB_OK;
-    if (cudaStreamCreateWithFlags(&p->own_st, cudaStreamNonBlocking) != cudaSuccess) rc = QB_ERR_CUDA;
-    if (!rc && (cudaStreamCreateWithFlags(&p->side_st, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)) rc = QB_ERR_CUDA;
+    // OSD streams run at a higher priority than the streams that carry sampling and min-sum: when both have CTAs ready
+    // (next batch's min-sum against this batch's OSD tail) the tail goes first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int w = 0; w < 2 && !rc; ++w) {
+        qb_workspace &W = p->ws[w];
+        if (cudaStreamCreateWithPriority(&W.own_st, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&W.side_st, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&W.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&W.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&W.ev_ms_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&W.ev_osd_done, cudaEventDisableTiming) != cudaSuccess) rc = QB_ERR_CUDA;
+        W.st = W.own_st;
+    }
+    if (!rc && (cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming) != cudaSuccess)) rc = QB_ERR_CUDA;
+    p->own_st = p->ws[0].own_st;
     p->st = p->own_st;
-#define AL(ptr, cnt) if (!rc) rc = dalloc(p, &p->ptr, cnt);
-    AL(synZ, B * gz.mw) AL(synX, B * gx.mw) AL(trueZ, B) AL(trueX, B) AL(hardZ, B * gz.nw) AL(hardX, B * gx.nw)
-    AL(convZ, B) AL(convX, B) AL(flags, B) AL(itZ, B) AL(itX, B) AL(failZ, B) AL(failX, B) AL(nfail, 2)
-    AL(fwZ, B) AL(fwX, B) AL(sortZ, B) AL(sortX, B)
-    AL(postZ, B * gz.n) AL(postX, B * gx.n) AL(counts, 8) AL(ev_ptr, B + 1) AL(syn8, B * std::max(gz.m, gx.m))
-    AL(osdinfoZ, B) AL(osdinfoX, B)
+    // the second workspace costs a second set of posterior buffers (B x n floats per side): skipped for tiny pipelines
+    // only when memory is short
+    for (int w = 0; w < 2; ++w) {
+        qb_workspace &W = p->ws[w];
+#define AL(ptr, cnt) if (!rc) rc = dalloc(p, &W.ptr, cnt);
+        AL(synZ, B * gz.mw) AL(synX, B * gx.mw) AL(trueZ, B) AL(trueX, B) AL(hardZ, B * gz.nw) AL(hardX, B * gx.nw)
+        AL(convZ, B) AL(convX, B) AL(flags, B) AL(itZ, B) AL(itX, B) AL(failZ, B) AL(failX, B) AL(nfail, 2)
+        AL(fwZ, B) AL(fwX, B) AL(sortZ, B) AL(sortX, B)
+        AL(postZ, B * gz.n) AL(postX, B * gx.n) AL(osdinfoZ, B) AL(osdinfoX, B)
 #undef AL
+    }
+    if (!rc) rc = dalloc(p, &p->counts, 8);
+    if (!rc) rc = dalloc(p, &p->ev_ptr, B + 1);
+    if (!rc) rc = dalloc(p, &p->syn8, B * std::max(gz.m, gx.m));
     if (!rc) {
         p->evs.resize((size_t)MAX_TIMED_BATCHES * EV_PER_BATCH);
         for (auto &e : p->evs) if (cudaEventCreate(&e) != cudaSuccess) { rc = QB_ERR_CUDA; break; }
@@ -851,13 +913,18 @@ void qb_pipeline_destroy(qb_pipeline *p)
 {
     if (!p) return;
     cudaSetDevice(p->dz->device);
+    cudaDeviceSynchronize();
     for (void *q : p->owned) cudaFree(q);
     if (p->events) cudaFree(p->events);
     for (auto e : p->evs) if (e) cudaEventDestroy(e);
-    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-    if (p->ev_join) cudaEventDestroy(p->ev_join);
-    if (p->side_st) cudaStreamDestroy(p->side_st);
-    if (p->own_st) cudaStreamDestroy(p->own_st);
+    for (int w = 0; w < 2; ++w) {
+        qb_workspace &W = p->ws[w];
+        for (cudaEvent_t e : {W.ev_fork, W.ev_join, W.ev_ms_done, W.ev_osd_done}) if (e) cudaEventDestroy(e);
+        if (W.side_st) cudaStreamDestroy(W.side_st);
+        if (W.own_st) cudaStreamDestroy(W.own_st);
+    }
+    if (p->ev_begin) cudaEventDestroy(p->ev_begin);
+    if (p->ev_tail) cudaEventDestroy(p->ev_tail);
     delete p;
 }
 
@@ -865,6 +932,7 @@ int qb_pipeline_set_stream(qb_pipeline *p, void *stream, int use_external)
 {
     QB_REQUIRE(p != nullptr, "NULL argument");
     p->st = use_external ? static_cast<cudaStream_t>(stream) : p->own_st;
+    p->ws[0].st = p->st;
     return QB_OK;
 }
 
@@ -876,19 +944,18 @@ int qb_pipeline_run(qb_pipeline *p, uint64_t seed, uint64_t first_shot, int64_t 
     QB_REQUIRE(n_shots >= 0, "n_shots must be >= 0");
     if (int rc = check_cfg(cfg)) return rc;
     QB_CUDA(cudaSetDevice(p->dz->device));
-    p->stats = qb_pipeline_stats{};
-    if (int rc = prep_alpha(p, cfg)) return rc;
-    QB_CUDA(cudaMemsetAsync(p->counts, 0, 8 * sizeof(int64_t), p->st));
+    if (int rc = begin_run(p, cfg)) return rc;
     int nb = 0;
     for (int64_t done = 0; done < n_shots; done += p->max_batch, ++nb) {
         const int B = (int)std::min<int64_t>(p->max_batch, n_shots - done);
-        if (nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_START], p->st));
-        if (int rc = launch_sample_syndrome(p->s, seed, first_shot + (uint64_t)done, B, error_rate, p->synZ, p->trueZ,
-                                            p->synX, p->trueX, nullptr, p->st)) return rc;
+        qb_workspace &W = p->ws[nb & 1], &O = p->ws[(nb & 1) ^ 1];
+        if (nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_START], W.st));
+        if (int rc = launch_sample_syndrome(p->s, seed, first_shot + (uint64_t)done, B, error_rate, W.synZ, W.trueZ,
+                                            W.synX, W.trueX, nullptr, W.st)) return rc;
         p->stats.kernel_launches++;
-        if (nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_SAMPLED], p->st));
-        if (int rc = decode_batch(p, B, cfg, nb)) return rc;
-        if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h + done, p->flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+        if (nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_SAMPLED], W.st));
+        if (int rc = decode_batch(p, W, O, B, cfg, nb)) return rc;
+        if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h + done, W.flags, (size_t)B, cudaMemcpyDeviceToHost, W.st));
     }
     return finish_run(p, nb, counts_h);
 }
@@ -912,23 +979,23 @@ int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const u
         QB_CUDA(cudaMalloc(&p->events, (nev + nev / 2 + 1024) * 4));
         p->ev_cap = nev + nev / 2 + 1024;
     }
-    if (int rc = prep_alpha(p, cfg)) return rc;
-    QB_CUDA(cudaMemsetAsync(p->counts, 0, 8 * sizeof(int64_t), p->st));
+    if (int rc = begin_run(p, cfg)) return rc;
+    qb_workspace &W = p->ws[0];
     QB_CUDA(cudaEventRecord(p->evs[EV_START], p->st));
     QB_CUDA(cudaMemcpyAsync(p->ev_ptr, ev_ptr_h, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, p->st));
     if (nev) QB_CUDA(cudaMemcpyAsync(p->events, events_h, nev * 4, cudaMemcpyHostToDevice, p->st));
-    if (int rc = launch_events_syndrome(p->s, p->ev_ptr, p->events, B, p->synZ, p->trueZ, p->synX, p->trueX, p->st)) return rc;
+    if (int rc = launch_events_syndrome(p->s, p->ev_ptr, p->events, B, W.synZ, W.trueZ, W.synX, W.trueX, p->st)) return rc;
     p->stats.kernel_launches++;
     QB_CUDA(cudaEventRecord(p->evs[EV_SAMPLED], p->st));
-    if (int rc = decode_batch(p, B, cfg, 0)) return rc;
-    if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, p->flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+    if (int rc = decode_batch(p, W, p->ws[1], B, cfg, 0)) return rc;
+    if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, W.flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
     if (converged_h) {
-        QB_CUDA(cudaMemcpyAsync(converged_h, p->convZ, (size_t)B, cudaMemcpyDeviceToHost, p->st));
-        QB_CUDA(cudaMemcpyAsync(converged_h + B, p->convX, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+        QB_CUDA(cudaMemcpyAsync(converged_h, W.convZ, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+        QB_CUDA(cudaMemcpyAsync(converged_h + B, W.convX, (size_t)B, cudaMemcpyDeviceToHost, p->st));
     }
     if (final_iter_h) {
-        QB_CUDA(cudaMemcpyAsync(final_iter_h, p->itZ, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
-        QB_CUDA(cudaMemcpyAsync(final_iter_h + B, p->itX, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
+        QB_CUDA(cudaMemcpyAsync(final_iter_h, W.itZ, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
+        QB_CUDA(cudaMemcpyAsync(final_iter_h + B, W.itX, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
     }
     return finish_run(p, 1, counts_h);
 }
@@ -944,19 +1011,19 @@ int qb_pipeline_decode_host(qb_pipeline *p, const int8_t *sparseZ_h, const uint3
     p->stats = qb_pipeline_stats{};
     if (B == 0) { memset(counts_h, 0, 8 * sizeof(int64_t)); return QB_OK; }
     const GraphDev &gz = p->dz->g, &gx = p->dx->g;
-    if (int rc = prep_alpha(p, cfg)) return rc;
-    QB_CUDA(cudaMemsetAsync(p->counts, 0, 8 * sizeof(int64_t), p->st));
+    if (int rc = begin_run(p, cfg)) return rc;
+    qb_workspace &W = p->ws[0];
     QB_CUDA(cudaEventRecord(p->evs[EV_START], p->st));
     QB_CUDA(cudaMemcpyAsync(p->syn8, sparseZ_h, (size_t)B * gz.m, cudaMemcpyHostToDevice, p->st));
-    if (int rc = launch_pack_bits(p->syn8, B, gz.m, p->synZ, gz.mw, p->st)) return rc;
+    if (int rc = launch_pack_bits(p->syn8, B, gz.m, W.synZ, gz.mw, p->st)) return rc;
     QB_CUDA(cudaMemcpyAsync(p->syn8, sparseX_h, (size_t)B * gx.m, cudaMemcpyHostToDevice, p->st));
-    if (int rc = launch_pack_bits(p->syn8, B, gx.m, p->synX, gx.mw, p->st)) return rc;
-    QB_CUDA(cudaMemcpyAsync(p->trueZ, trueZ_h, (size_t)B * 4, cudaMemcpyHostToDevice, p->st));
-    QB_CUDA(cudaMemcpyAsync(p->trueX, trueX_h, (size_t)B * 4, cudaMemcpyHostToDevice, p->st));
+    if (int rc = launch_pack_bits(p->syn8, B, gx.m, W.synX, gx.mw, p->st)) return rc;
+    QB_CUDA(cudaMemcpyAsync(W.trueZ, trueZ_h, (size_t)B * 4, cudaMemcpyHostToDevice, p->st));
+    QB_CUDA(cudaMemcpyAsync(W.trueX, trueX_h, (size_t)B * 4, cudaMemcpyHostToDevice, p->st));
     p->stats.kernel_launches += 2;
     QB_CUDA(cudaEventRecord(p->evs[EV_SAMPLED], p->st));
-    if (int rc = decode_batch(p, B, cfg, 0)) return rc;
-    if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, p->flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+    if (int rc = decode_batch(p, W, p->ws[1], B, cfg, 0)) return rc;
+    if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, W.flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
     return finish_run(p, 1, counts_h);
 }
 
@@ -971,15 +1038,16 @@ int qb_pipeline_last_batch_detail(qb_pipeline *p, int32_t side, uint32_t *hard_b
 {
     QB_REQUIRE(p != nullptr && (side == 0 || side == 1), "bad argument");
     QB_CUDA(cudaSetDevice(p->dz->device));
-    QB_CUDA(cudaStreamSynchronize(p->st));
+    QB_CUDA(cudaDeviceSynchronize());
     const size_t B = (size_t)p->last_B;
     if (B == 0) return QB_OK;
+    const qb_workspace &W = p->ws[p->last_ws];
     const GraphDev &g = side ? p->dx->g : p->dz->g;
-    if (hard_bits_h) QB_CUDA(cudaMemcpy(hard_bits_h, side ? p->hardX : p->hardZ, B * g.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (post_h) QB_CUDA(cudaMemcpy(post_h, side ? p->postX : p->postZ, B * g.n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (hard_bits_h) QB_CUDA(cudaMemcpy(hard_bits_h, side ? W.hardX : W.hardZ, B * g.nw * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (post_h) QB_CUDA(cudaMemcpy(post_h, side ? W.postX : W.postZ, B * g.n * sizeof(float), cudaMemcpyDeviceToHost));
     if (osd_info_h) {
         QB_REQUIRE(p->detail, "per-shot OSD information is recorded only after qb_pipeline_enable_detail(p, 1)");
-        QB_CUDA(cudaMemcpy(osd_info_h, side ? p->osdinfoX : p->osdinfoZ, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        QB_CUDA(cudaMemcpy(osd_info_h, side ? W.osdinfoX : W.osdinfoZ, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
     }
     return QB_OK;
 }

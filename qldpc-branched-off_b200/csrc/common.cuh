@@ -146,6 +146,8 @@ int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st);
 bool osd_free_applicable(const qb_decoder *dec);
 int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d, int32_t **ovf_idx_d, cudaStream_t st);
 int osd_free_stats(qb_decoder *dec, int32_t *out10);
+// kernels one launch_osd0 call issues for a pipeline queue (gpu_launches accounting)
+int osd_launches_per_call(const qb_decoder *dec);
 // order the failure queue by descending residual weight (longest elimination first)
 int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const int32_t *n_fail_d, int32_t *sorted_idx, cudaStream_t st);
 

@@ -595,6 +595,8 @@ int launch_sort_failures(const int32_t *fail_idx, const int32_t *fail_wt, const 
     return QB_OK;
 }
 
+int osd_launches_per_call(const qb_decoder *dec) { return osd_free_applicable(dec) ? 5 : 1; }   // select, tier A, select 2, tier B, full-width
+
 int launch_osd0(qb_decoder *dec, const OsdLaunch &a, cudaStream_t st)
 {
     if (a.F <= 0) return QB_OK;
