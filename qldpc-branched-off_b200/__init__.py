@@ -8,7 +8,8 @@ fallback: importing a compute entry point without the built library raises.
 """
 __version__ = "0.1.0"
 
-_SRC_MODULES = ("codes", "codes.bb_code", "noise", "noise.builder", "noise.compiled", "noise.simulation",
+_SRC_MODULES = ("codes", "codes.bb_code", "noise", "noise.builder", "noise.compiled", "noise.simulation", "noise.model",
+                "noise.kernels", "noise.constants",
                 "decoding", "decoding.sparse", "decoding.dense", "decoding.osd", "decoding.kernels",
                 "simulation", "simulation.engine", "utils", "utils.caching", "utils.plotting", "decoding.alpha", "decoding.scopt")
 

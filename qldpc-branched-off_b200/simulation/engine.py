@@ -62,6 +62,35 @@ def _dist():
     return None, 0, 1
 
 
+class _Progress:
+    """Batch-level stand-in for the reference's per-trial rich progress bar (engine.py:436-460): the same line
+    ``p=... | logical=<errors>/<target>``, advanced once per device round instead of once per shot."""
+
+    def __init__(self, error_rate, total, target, enabled=True):
+        self.bar = self.task = None
+        if not enabled:
+            return
+        try:
+            from rich.progress import BarColumn, Progress, TaskProgressColumn, TextColumn, TimeElapsedColumn
+            self.bar = Progress(TextColumn("p={task.fields[p]:.4g} | logical={task.fields[errors]}/{task.fields[target]}", justify="left"),
+                                BarColumn(), TaskProgressColumn(), TimeElapsedColumn())
+            self.bar.start()
+            self.task = self.bar.add_task("simulate", total=total, p=error_rate, errors=0, target=(target if target else "∞"))
+        except Exception:          # rich missing or no usable console: log lines instead
+            self.bar = None
+            self.p, self.total, self.target = error_rate, total, target
+
+    def update(self, trials, errors, estimate=False):
+        if self.bar is not None:
+            self.bar.update(self.task, completed=trials, errors=(f"~{errors}" if estimate else errors))
+        elif hasattr(self, "p"):
+            _logger.info("p=%.4g | logical=%s/%s | %d/%d shots", self.p, errors, self.target or "∞", trials, self.total)
+
+    def close(self):
+        if self.bar is not None:
+            self.bar.stop()
+
+
 class ShotEngine:
     """Device state of one (code, p): sampler, two decoders, pipeline."""
 
@@ -142,7 +171,7 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
                    use_dynamic_alpha=True, alpha_mode=None, alvarado_alpha=None, alpha_estimation_trials=5000,
                    alpha_estimation_bins=50, precomputed_matrices=None, num_workers=None, base_seed=None,
                    use_jit=True, target_logical_errors=None, max_trials=None, scopt=False,
-                   estimation_plot_dir=None, batch_size=None, **bb_params):
+                   estimation_plot_dir=None, batch_size=None, progress=True, **bb_params):
     if base_seed is None:
         base_seed = np.random.randint(0, 2 ** 31)
     if alpha_mode not in (None, "dynamical", "alvarado", "alvarado-autoregressive"):
@@ -185,26 +214,44 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
         batch_size = int(min(65536, max(256, -(-max_trials // world))))
     eng = ShotEngine(compiled, Lx, Lz, matrices, max_batch=batch_size)
     cfg = _lib.make_config(maxIter, qmode, alpha_z, alpha_x, clip_llr=20.0, use_osd=True)
+    report = _Progress(error_rate, max_trials, target_logical_errors if stop_on_errors else None, enabled=progress and rank == 0)
     try:
         z_errs = x_errs = tot_errs = trials_run = 0
         done = 0
-        while done < max_trials:
-            round_total = min(world * batch_size, max_trials - done)
-            lo, hi = shard_range(round_total, rank, world)
-            counts, flags = eng.pipeline.run(base_seed, done + lo, hi - lo, error_rate, cfg, want_flags=stop_on_errors)
-            if stop_on_errors:
+        if stop_on_errors:
+            # early stop: per round the per-shot flags of all ranks are gathered and replayed in shot order, which gives
+            # the reference's exact cut (engine.py:450-464)
+            while done < max_trials:
+                round_total = min(world * batch_size, max_trials - done)
+                lo, hi = shard_range(round_total, rank, world)
+                counts, flags = eng.pipeline.run(base_seed, done + lo, hi - lo, error_rate, cfg, want_flags=True)
                 all_flags = _gather_flags(dist, world, flags, round_total)
                 cut = early_stop_cut(all_flags & 3, target_logical_errors, tot_errs)
                 use = all_flags[:cut] if cut is not None else all_flags
                 z_errs += int(np.sum(use & 1 != 0)); x_errs += int(np.sum(use & 2 != 0)); tot_errs += int(np.sum(use != 0))
                 trials_run += len(use)
+                report.update(trials_run, tot_errs)
                 if cut is not None:
                     break
-            else:
-                c = _reduce_counts(dist, counts)
-                z_errs += int(c[0]); x_errs += int(c[1]); tot_errs += int(c[2]); trials_run += int(c[3])
-            done += round_total
+                done += round_total
+        else:
+            # fixed number of shots: no synchronisation between ranks inside the loop.  Every rank owns one contiguous
+            # range of shot indices and walks it in chunks of a few batches (one library call each: the batches of a call
+            # are pipelined on the device, the host only updates the progress line in between); the counters are reduced
+            # once at the end.
+            lo, hi = shard_range(max_trials, rank, world)
+            local = np.zeros(8, dtype=np.int64)
+            chunk = batch_size * max(1, min(32, (1 << 21) // batch_size))
+            for start in range(lo, hi, chunk):
+                n = min(chunk, hi - start)
+                counts, _ = eng.pipeline.run(base_seed, start, n, error_rate, cfg)
+                local += counts
+                report.update(min(max_trials, int(local[3]) * world), int(local[2]) * world, estimate=world > 1)
+            c = _reduce_counts(dist, local)
+            z_errs, x_errs, tot_errs, trials_run = int(c[0]), int(c[1]), int(c[2]), int(c[3])
+            report.update(trials_run, tot_errs)
     finally:
+        report.close()
         eng.close()
     result = {
         "logical_error_rate": tot_errs / max(1, trials_run),

@@ -603,3 +603,103 @@ def test_scopt_beta_vs_reference_golden_and_run_simulation():
     for k in ("beta_z", "beta_x", "beta_r2_z", "beta_r2_x", "logical_error_rate", "num_trials"):
         assert k in res
     assert res["num_trials"] == 512 and -1.0 < res["beta_z"] < 0.0 and -1.0 < res["beta_x"] < 0.0
+
+
+# ---- main.py's call sequence on the GPU backend ---------------------------------------------------------
+def test_main_py_call_sequence_on_the_gpu(tmp_path, monkeypatch):
+    """The reference's main.py:56-151, statement by statement, through the ``src.*`` aliases installed by
+    install_as_src() (the GPU box has no reference checkout, so the script itself cannot be executed there; the CPU test
+    test_unmodified_reference_main_runs_up_to_the_gpu_boundary runs the real file up to the first device call, and
+    tools/run_reference_main.py runs it end to end wherever both are present): code file from the generator, cache
+    lookup / build / save, run_simulation with main.py's keyword arguments (alvarado-autoregressive, osd_order=2,
+    target_logical_errors, max_trials), the three plotting calls and the results.npz layout of main.py:140-147."""
+    import importlib
+    qldpc_b200.install_as_src()
+    BBCodeCircuit = importlib.import_module("src.codes.bb_code").BBCodeCircuit
+    run_simulation = importlib.import_module("src.simulation.engine").run_simulation
+    build_decoding_matrices = importlib.import_module("src.noise.builder").build_decoding_matrices
+    plotting = importlib.import_module("src.utils.plotting")
+    caching = importlib.import_module("src.utils.caching")
+    from qldpc_b200.codes.generate import write_code_npz
+    monkeypatch.chdir(tmp_path)
+    write_code_npz("[[72, 12, 6]]", "codes")
+    experiments = [{"code": "[[72, 12, 6]]", "name": "72", "physicalErrorRates": [0.006], "distance": 6}]
+    target_logical_errors, max_trials, maxIter, osd_order, num_workers = 30, 20, 20, 2, 8      # main.py:41-45
+    alpha_mode, scopt, cache_dir = "alvarado-autoregressive", False, "matrix_cache"
+    output_dir = os.path.join("output", "run_test"); os.makedirs(output_dir)
+    estimation_plot_dir = os.path.join(output_dir, "estimation_plots"); os.makedirs(estimation_plot_dir)
+    results = {}
+    for exp in experiments:
+        data = np.load(f"codes/{exp['code']}.npz")
+        Hx, Hz, Lx, Lz = data["Hx"], data["Hz"], data["Lx"], data["Lz"]
+        bb_params = {k: data[k] for k in ["ell", "m", "a_x_powers", "a_y_powers", "b_y_powers", "b_x_powers"] if k in data}
+        results[exp["name"]] = {}
+        cb = BBCodeCircuit(Hx, Hz, num_cycles=exp["distance"], **bb_params)
+        for p in exp["physicalErrorRates"]:
+            key = caching.compute_cache_key(Hx, Hz, Lx, Lz, exp["distance"], p)
+            matrices_ = caching.load_matrices(cache_dir, key)
+            assert matrices_ is None
+            matrices_ = build_decoding_matrices(cb, Lx, Lz, p, num_workers=num_workers)
+            caching.save_matrices(cache_dir, key, matrices_)
+            assert caching.load_matrices(cache_dir, key) is not None
+            res = run_simulation(Hx, Hz, Lx, Lz, p, num_cycles=exp["distance"], maxIter=maxIter, osd_order=osd_order,
+                                 precomputed_matrices=matrices_, alpha_mode=alpha_mode, num_workers=num_workers,
+                                 target_logical_errors=target_logical_errors, max_trials=max_trials, scopt=scopt,
+                                 estimation_plot_dir=estimation_plot_dir, alpha_estimation_trials=200, **bb_params)
+            results[exp["name"]][p] = res
+    res = results["72"][0.006]
+    assert res["num_trials"] == max_trials and 0 <= res["logical_errors"] <= max_trials       # main.py's max_trials = 20
+    assert len(res["alpha_values_z"]) == maxIter and len(res["alpha_r2_values_x"]) == maxIter
+    plotting.plot_simulation_results(results, f"{output_dir}/simulation_results.png")
+    plotting.plot_alpha_comparison(results, f"{output_dir}/alpha_comparison.png")
+    alpha_r2_values = plotting.plot_alpha_linearity(results, f"{output_dir}/alpha_linearity.png")
+    alpha_values = {c: {p: {"z": r.get("alpha_values_z"), "x": r.get("alpha_values_x")} for p, r in d.items()} for c, d in results.items()}
+    np.savez(f"{output_dir}/results.npz", results=results, alpha_values=alpha_values, beta_values={}, alpha_r2_values=alpha_r2_values,
+             estimation_r2_values={})
+    back = np.load(f"{output_dir}/results.npz", allow_pickle=True)
+    assert set(back.files) == {"results", "alpha_values", "beta_values", "alpha_r2_values", "estimation_r2_values"}
+    assert back["results"].item()["72"][0.006]["num_trials"] == max_trials
+
+
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import helpers, qldpc_b200
+from qldpc_b200.simulation.engine import run_simulation
+rank = int(os.environ["RANK"])
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+s = helpers.code_setup("72"); p = 0.006; M = helpers.matrices("72", p)
+kw = dict(num_cycles=6, maxIter=20, precomputed_matrices=M, alpha_mode="dynamical", progress=False, **s["bb"])
+a = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=6000, base_seed=11, batch_size=1024, **kw)
+b = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, base_seed=11, target_logical_errors=40, max_trials=6000, batch_size=512, **kw)
+c = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=2000, base_seed=None, batch_size=512, **kw)    # seed drawn on rank 0
+out = [None] * dist.get_world_size()
+dist.all_gather_object(out, (a, b, c))
+if rank == 0:
+    assert all(o == out[0] for o in out), out
+    np.save(sys.argv[2], np.array([a["logical_errors"], a["num_trials"], b["logical_errors"], b["num_trials"]]))
+dist.destroy_process_group()
+"""
+
+
+def test_run_simulation_two_ranks_nccl(tmp_path):
+    """ADVICE (round 1): run_simulation under torchrun with NCCL -- collective tensors on each rank's own GPU, the seed
+    broadcast from rank 0 when None, results identical on every rank and identical to a single-process run (shot
+    streams are keyed by the global shot index), including the in-order early stop."""
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from qldpc_b200.simulation.engine import run_simulation
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"; script.write_text(_NCCL_WORKER)
+    outfile = str(tmp_path / "out.npy")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script), root, outfile], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    two = np.load(outfile)
+    s = code_setup("72"); p = 0.006; M = matrices("72", p)
+    kw = dict(num_cycles=6, maxIter=20, precomputed_matrices=M, alpha_mode="dynamical", progress=False, **s["bb"])
+    a = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=6000, base_seed=11, batch_size=4096, **kw)
+    b = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, base_seed=11, target_logical_errors=40, max_trials=6000, batch_size=700, **kw)
+    assert [a["logical_errors"], a["num_trials"], b["logical_errors"], b["num_trials"]] == two.tolist()

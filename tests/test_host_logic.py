@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import code_setup
+from helpers import builder_hashes, code_setup
 import qldpc_b200  # noqa: F401
 from qldpc_b200 import _lib
 
@@ -229,3 +229,79 @@ def test_edge_layout_generic_graphs():
     assert s["ok"] == 0
     # non-finite prior: not usable
     assert _layout_stats(np.eye(3, dtype=np.int8), [1.0, np.inf, 1.0])["ok"] == 0
+
+
+def test_noise_kernel_twins_match_oracle():
+    """src.noise.kernels / .model / .constants aliases: the array-interface twins compose to the reference's
+    run_trial_fast (simulation.py:21-107), checked against the C oracle (itself pinned to the real reference)."""
+    import qldpc_b200
+    from qldpc_b200.noise import kernels as K, constants as Cn, model
+    from oracle import oracle as orc
+    s = code_setup("72"); cc = s["cc"]; p = 0.02
+    assert Cn.GATE_TO_OPCODE["CNOT"] == 1 and Cn.GATE_TO_OPCODE["ZX"] == 26 and Cn.OP_IDLE == 6 and callable(model.generate_noisy_circuit)
+    src = qldpc_b200.install_as_src()
+    import importlib
+    assert importlib.import_module("src.noise.kernels") is K and importlib.import_module("src.noise.constants") is Cn
+    assert importlib.import_module("src.noise.model") is model
+    n = cc.num_error_locs
+    rng = np.random.default_rng(4)
+    for _ in range(3):
+        rv = rng.random(n); rp = rng.integers(0, 3, n).astype(np.int32); r2 = rng.integers(0, 15, n).astype(np.int32)
+        out = [np.empty(2 * n + 8, dtype=np.int32) for _ in range(3)]
+        ln = K.generate_noisy_circuit_jit(cc.base_ops, cc.base_q1, cc.base_q2, p, rv, rp, r2, *out)
+        ops = np.concatenate([out[0][:ln], cc.suffix_ops]); q1 = np.concatenate([out[1][:ln], cc.suffix_q1]); q2 = np.concatenate([out[2][:ln], cc.suffix_q2])
+        hz, stz, nz, ez = K.simulate_circuit_Z_jit(ops, q1, q2, cc.total_qubits, None, None, cc.num_meas_x + 100)
+        hx, stx, nx, ex = K.simulate_circuit_X_jit(ops, q1, q2, cc.total_qubits, None, None, cc.num_meas_z + 100)
+        fired = int((rv < p).sum())
+        assert nz == cc.num_meas_x and nx == cc.num_meas_z and 0 < ez <= fired and 0 < ex <= fired and ez + ex >= fired
+        sz = K.sparsify_syndrome_jit(hz, nz, cc.x_syn_positions, cc.x_syn_ptrs, cc.num_x_checks)
+        sx = K.sparsify_syndrome_jit(hx, nx, cc.z_syn_positions, cc.z_syn_ptrs, cc.num_z_checks)
+        tz = (s["Lx"].astype(int) @ K.extract_data_state_jit(stz, cc.data_qubit_indices)) % 2
+        tx = (s["Lz"].astype(int) @ K.extract_data_state_jit(stx, cc.data_qubit_indices)) % 2
+        osz, otz, osx, otx = orc.run_trial_arrays(cc, p, s["Lx"], s["Lz"], rv, rp, r2)
+        assert np.array_equal(sz, osz) and np.array_equal(sx, osx) and np.array_equal(tz, otz) and np.array_equal(tx, otx)
+
+
+def test_code_generator_matches_reference_format_and_logicals_are_valid_for_all_codes(tmp_path):
+    """generate_codes.py:154-168 without qldpc: same keys / dtypes / Hx, Hz as the reference's shipped files (hashes
+    recorded from them by make_golden.py), and own logical operators that are valid for all five codes."""
+    from qldpc_b200.codes.generate import KEYS, generate_all
+    from qldpc_b200.utils.gf2 import rank
+    import hashlib
+    paths = generate_all(str(tmp_path))
+    assert len(paths) == 5
+    hashes = builder_hashes()
+    for path in paths:
+        name = os.path.basename(path)[:-4]
+        d = np.load(path)
+        assert tuple(d.files) == KEYS
+        Hx, Hz, Lx, Lz = d["Hx"], d["Hz"], d["Lx"], d["Lz"]
+        assert Hx.dtype == np.int64 and Lx.dtype == np.uint8 and d["distance"].shape == () and d["a_x_powers"].dtype == np.int64
+        ref = hashes[name]
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        assert sha(Hx) == ref["Hx"] and sha(Hz) == ref["Hz"] and int(d["distance"]) == ref["distance"]
+        k = ref["k"]
+        assert Lx.shape == (k, Hx.shape[1]) and Lz.shape == (k, Hx.shape[1])
+        Lxi, Lzi = Lx.astype(np.int64), Lz.astype(np.int64)
+        assert not ((Hz @ Lxi.T) % 2).any() and not ((Hx @ Lzi.T) % 2).any(), name       # commute with the stabilisers
+        assert np.array_equal((Lxi @ Lzi.T) % 2, np.eye(k, dtype=np.int64)), name          # symplectic pairs
+        assert rank(np.vstack([Hx, Lxi])) == rank(Hx) + k and rank(np.vstack([Hz, Lzi])) == rank(Hz) + k, name
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/main.py"), reason="reference checkout not present")
+def test_unmodified_reference_main_runs_up_to_the_gpu_boundary(tmp_path):
+    """the reference's main.py, unmodified, under install_as_src(): every import of main.py:1-10 resolves,
+    codes/*.npz from our generator load, compute_cache_key / load_matrices / build_decoding_matrices / save_matrices run,
+    and run_simulation is entered with main.py's keyword arguments (main.py:83-88) -- in this container it must then stop
+    with the library's "no CUDA device" error (there is no CPU fallback).  The GPU half of the same sequence is
+    tests/test_gpu_parity.py::test_main_py_call_sequence_on_the_gpu."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import tools.run_reference_main as r\n"
+        "r.run('/root/reference', %r)\n" % (ROOT, str(tmp_path)))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode != 0
+    assert "no CUDA device" in res.stderr and "QbError" in res.stderr, res.stderr[-2000:]
+    assert "run_simulation" in res.stderr, "the failure must come from inside run_simulation"
+    assert os.path.isdir(tmp_path / "matrix_cache") and len(os.listdir(tmp_path / "matrix_cache")) == 1, "the built matrices were cached"
+    assert len(os.listdir(tmp_path / "codes")) == 5

@@ -15,7 +15,7 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("tag", ["72", "90", "108", "144"])
+@pytest.mark.parametrize("tag", ["72", "90", "108", "144", "288"])
 def test_builder_matches_reference_cache(tag):
     """Hx/Hz from the polynomials and HdecZ/X, channel_probs, HZ/HX_full of our bit-parallel
     builder hash-equal to the reference's codes/*.npz and matrix_cache/*.npz."""
