@@ -25,6 +25,9 @@ MAX_ITER = 20
 METRIC = "decoded shots/s ([[144,12,12]], p=0.005)"
 WORKLOAD = ("[[144,12,12]] gross code, circuit-level p=0.005, min-sum 20 it (dynamical alpha) + OSD-0 on "
             "non-converged sides, Z and X side per shot")
+# identical in both arms (the driver compares the two config dicts)
+CONFIG = {"workload": WORKLOAD, "code": CODE, "p": P, "max_iter": MAX_ITER, "alpha_mode": "dynamical", "osd_order": 0,
+          "shots": "both sides of every shot decoded; LER counts z_err or x_err (engine.py:122)"}
 
 
 def smi_sampler(stop, out, gpu_index):
@@ -63,11 +66,31 @@ def summarize_clocks(lines):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one minsum_edge_kernel launch, from the `ncu --set full` capture of
-# `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --shots-per-step 16384 --batch 16384`
-# (profiles/r1b_ncu_full_summary.txt): 3.3 MB + 507.8 MB for a 16384-shot launch = 31.2 KB per shot (the posteriors of the
-# non-converged sides, 0.946 x 8857 x 4 B, dominate: no re-reads), scaled to the launch size.
-NCU_TRAFFIC_BYTES_PER_SHOT = (3.26e6 + 507.83e6) / 16384
+def ncu_traffic(kernel):
+    """Per-launch ncu counters of one kernel from profiles/r2_traffic.json (written by tools/ncu_traffic.py from an
+    `ncu --set full` capture of this file's own command line; the JSON records the command) -> (dict, shots per launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            d = json.load(f)
+        for name, k in d["kernels"].items():
+            if name.startswith(kernel):
+                return k, int(d["shots_per_launch"])
+    except Exception:
+        pass
+    return None, 0
+
+
+def reference_cpu_timing():
+    """The real (numba) reference timed on host cores.  /root/reference does not travel to the GPU box, so the record is
+    the measurement made in the build container (profiles/r2_reference_cpu_timing.json says how)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_reference_cpu_timing.json")) as f:
+            d = json.load(f)
+        return {"value": d["shots_per_s"], "unit": "shots/s", "cores": d["workers"], "kind": "reference",
+                "sample": f"{d['shots']} shots in {d['seconds']:.0f} s; {d['what']}", "where": d["where"],
+                "logical_error_rate": d["logical_error_rate"]}
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -100,7 +123,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shots_per_step": per_step},
+        "config": CONFIG, "shots_per_step": per_step,
         "cpu_baseline": {"value": value, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "logical_error_rate": tot_err / tot_n, "edge_messages_per_s": tot_em / tot_t,
@@ -119,6 +142,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-run-simulation", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly one JSON line: NCCL's own log lines (NCCL_DEBUG=VERSION/INFO on some boxes) go to stderr
@@ -172,33 +196,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step(i):
-        first = (i * world + rank) * B          # disjoint shot ranges per step and rank
-        counts, _ = eng.pipeline.run(seed, first, B, P, cfg)
+    # K steps = K device batches of B shots in ONE library call: the two batch workspaces of the pipeline overlap the
+    # sampling / min-sum of batch i+1 with the OSD-0 tail of batch i, and nothing synchronises with the host in between
+    def steps(first_step, k):
+        first = (first_step * world + rank * k) * B          # disjoint shot ranges per call and rank
+        counts, _ = eng.pipeline.run(seed, first, k * B, P, cfg)
         return counts, eng.pipeline.stats()
 
-    for i in range(args.warmup):
-        step(i)
+    if args.warmup:
+        steps(0, args.warmup)
     clock_lines, stop = [], threading.Event()
     th = threading.Thread(target=smi_sampler, args=(stop, clock_lines, local_rank), daemon=True)
     th.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = np.zeros(8, dtype=np.int64)
-    agg = dict(ms_sample=0.0, ms_minsum=0.0, ms_osd=0.0, ms_logical=0.0, kernel_launches=0, edge_messages=0, osd_sides=0, batches=0)
     t_wall = time.perf_counter()
     ev0.record(stream)
-    for i in range(args.steps):
-        counts, st = step(args.warmup + i)
-        tot += counts
-        for k in agg:
-            if k in st:
-                agg[k] += st[k]
-        agg["batches"] += -(-B // args.batch)
+    tot, st = steps(args.warmup, args.steps)
     ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall
     stop.set()
+    launches_timed = int(st["kernel_launches"])
+    # per-stage and per-kernel durations come from two extra single-batch calls after the timed region: inside the
+    # pipelined call the stages of consecutive batches overlap, so their event-to-event times contain each other
+    agg = dict(ms_sample=0.0, ms_minsum=0.0, ms_osd=0.0, ms_logical=0.0, kernel_launches=0, edge_messages=0, osd_sides=0)
+    n_stage = 2
+    for j in range(n_stage):
+        _, st1 = steps(args.warmup + args.steps + j, 1)
+        for k in agg:
+            agg[k] += st1[k]
+    agg["batches"] = n_stage * -(-B // args.batch)
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     ctot = torch.from_numpy(tot.copy()).to(dev)
@@ -251,6 +279,27 @@ def main():
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(te_t.item())
 
+    # ---- e2e through the public entry point a user of the reference calls: run_simulation(num_trials=2**20, ...) ----
+    # wall clock of the whole call on this rank's GPU: host table build (fault signatures, priors), handle creation,
+    # 2**20 shots (Philox), counters back.  N = 1 only (under torchrun the entry point shards shots over the ranks itself).
+    e2e_rs = None
+    if world == 1 and not args.no_run_simulation:
+        from qldpc_b200.simulation.engine import run_simulation
+        n_rs = 1 << 20
+        t0 = time.perf_counter()
+        res = run_simulation(code["Hx"], code["Hz"], code["Lx"], code["Lz"], P, num_trials=n_rs, num_cycles=d, maxIter=MAX_ITER,
+                             osd_order=0, alpha_mode="dynamical", base_seed=seed, progress=False, **bb)
+        dt_all = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        res2 = run_simulation(code["Hx"], code["Hz"], code["Lx"], code["Lz"], P, num_trials=n_rs, num_cycles=d, maxIter=MAX_ITER,
+                              osd_order=0, alpha_mode="dynamical", base_seed=seed, precomputed_matrices=M, progress=False, **bb)
+        dt_pre = time.perf_counter() - t0
+        e2e_rs = {"value": n_rs / dt_all, "unit": "shots/s", "shots": n_rs, "seconds": dt_all,
+                  "with_precomputed_matrices": {"value": n_rs / dt_pre, "seconds": dt_pre},
+                  "logical_error_rate": res["logical_error_rate"], "same_result_both_calls": res == res2,
+                  "path": "qldpc_b200.simulation.engine.run_simulation(num_trials=2**20, maxIter=20, alpha_mode='dynamical', osd_order=0): "
+                          "wall clock of the whole call incl. host-side table build and handle creation"}
+
     if rank == 0:
         clocks = summarize_clocks(clock_lines)
         hbm_peak, peak_src = measured_peaks()
@@ -261,43 +310,61 @@ def main():
         ms_launch = agg["ms_minsum"] / max(1, n_ms_launch)
         shots_per_launch = min(args.batch, B)
         gz, gx = eng.decZ, eng.decX
-        # algorithmic HBM bytes of one min-sum launch: syndrome words in, hard bits + flags out,
-        # posteriors out only for non-converged sides
         nonconv_frac = (ctot[4] + ctot[5]) / max(1, 2 * ctot[3])
+        # algorithmic units of one launch: edge-messages = nnz x iterations executed, 8 B each on chip;
+        # HBM: syndrome words in, hard bits + flags out, posteriors out only for non-converged sides
+        em_per_s = agg["edge_messages"] / (agg["ms_minsum"] * 1e-3) if agg["ms_minsum"] > 0 else 0.0
+        em_per_launch = agg["edge_messages"] / max(1, n_ms_launch)
         per_shot = 0.5 * ((gz.m + 31) // 32 * 4 + (gx.m + 31) // 32 * 4) + 0.5 * ((gz.n + 31) // 32 * 4 + (gx.n + 31) // 32 * 4) + 5 \
             + nonconv_frac * 0.5 * (gz.n + gx.n) * 4
         hbm_bytes_launch = per_shot * shots_per_launch
-        achieved = hbm_bytes_launch / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
-        em_per_s = agg["edge_messages"] / (agg["ms_minsum"] * 1e-3) if agg["ms_minsum"] > 0 else 0.0
+        hbm_achieved = hbm_bytes_launch / (ms_launch * 1e-3) / 1e9 if ms_launch > 0 else 0.0
         sm_mhz = clocks["sm_mhz"] or 1965.0
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s: 128 B/clk/SM
+        ncu, ncu_shots = ncu_traffic("minsum_edge_kernel")
+        scale = shots_per_launch / ncu_shots if ncu_shots else 0.0
         out = {
             "metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "shots_per_step_per_gpu": B, "batch": args.batch, "max_iter": MAX_ITER,
-                       "sampler": "Philox4x32-10 on device, counter = global shot index",
-                       "l2": "no flush needed: per-batch posterior/state buffers (>1 GB) exceed the 126 MB L2 and every step decodes new shots"},
-            "roofline": {"bound": "hbm", "kernel": "minsum_edge_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_SHOT * shots_per_launch, "traffic_unit": "bytes/launch (ncu dram read+write of a 16384-shot launch, scaled per shot; profiles/)",
-                         "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
-                         "ms_per_launch": ms_launch, "shots_per_launch": shots_per_launch,
-                         "note": "HBM is not the binding resource by design (messages stay in shared memory); see roofline_smem"},
-            "roofline_smem": {"bound": "smem", "kernel": "minsum_edge_kernel", "edge_messages_per_s": em_per_s,
-                              "achieved": em_per_s * 8 / 1e9, "peak": smem_peak, "unit": "GB/s", "frac": em_per_s * 8 / 1e9 / smem_peak,
-                              "bytes_per_edge_message": 8, "peak_source": "148 SMs x 128 B/clk x median SM clock under load",
-                              "note": "SURVEY 8(d) algorithmic 8 B per edge-message; the kernel moves 16 B (two 4-byte gathers/scatters + the row-side LDS.128/STS.128) plus 2 B of slot index per edge-message, and is bound by the alu pipe (check rows) and by shared-memory instruction issue (variables), see DESIGN.md"},
+            "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "run": {"shots_per_step_per_gpu": B, "batch": args.batch, "steps_per_library_call": args.steps,
+                    "sampler": "Philox4x32-10 on device, counter = global shot index",
+                    "l2": "no flush needed: per-batch posterior/state buffers (>1 GB) exceed the 126 MB L2 and every step decodes new shots"},
+            # the binding roofline of the dominant kernel is on chip: algorithmic 8 B per edge-message against
+            # 148 SMs x 128 B/clk of shared-memory bandwidth at the SM clock sampled during the run
+            "roofline": {"bound": "smem", "kernel": "minsum_edge_kernel<1024,1>", "achieved": em_per_s * 8 / 1e9, "peak": smem_peak,
+                         "unit": "GB/s", "frac": em_per_s * 8 / 1e9 / smem_peak,
+                         "traffic": (ncu["smem_bytes"] * scale) if ncu else None,
+                         "traffic_unit": "bytes/launch: ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum x 128 B of a 16384-shot launch "
+                                         "(profiles/r2_traffic.json), scaled to this launch size",
+                         "algorithmic_bytes_per_launch": em_per_launch * 8, "edge_messages_per_launch": em_per_launch,
+                         "edge_messages_per_s": em_per_s, "bytes_per_edge_message": 8, "ms_per_launch": ms_launch,
+                         "shots_per_launch": shots_per_launch,
+                         "peak_source": "148 SMs x 128 B/clk x median SM clock under load (MEASURED_PEAKS.json holds HBM and tensor peaks only)",
+                         "issue_active_pct_ncu": ncu["issue_active_pct"] if ncu else None,
+                         "note": "the kernel moves 16 B + 2 B of slot index per edge-message through shared memory and is bound by the alu pipe "
+                                 "(check rows) and by shared-memory instruction issue (variables), DESIGN.md section 4"},
+            "roofline_hbm": {"bound": "hbm", "kernel": "minsum_edge_kernel<1024,1>", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_achieved / hbm_peak, "traffic": (ncu["dram_bytes"] * scale) if ncu else None,
+                             "traffic_unit": "bytes/launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r2_traffic.json), scaled",
+                             "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
+                             "note": "non-binding by design: messages never leave the SM; traffic = algorithmic bytes (posteriors of non-converged sides), no re-reads"},
             "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "shots_per_step": Be, "steps": e2e_steps,
-                    "path": "qb_pipeline_run_events_host: host-sampled fault events (pinned) -> H2D -> K2 -> min-sum -> OSD-0 -> logical check -> flags D2H"},
-            "gpu_launches": int(agg["kernel_launches"]),
+                    "path": "qb_pipeline_run_events_host (the C-ABI call behind run_trial_fast + the decoders): fault events sampled on the host "
+                            "BEFORE the timed region (three pinned sets, cycled) -> H2D -> K2 syndromes -> min-sum -> OSD-0 -> logical check -> "
+                            "flags D2H; contains no sampling work, one host synchronisation per step"},
+            "e2e_run_simulation": e2e_rs,
+            "gpu_launches": launches_timed,
             "clocks": clocks,
-            "stage_ms_per_step": {k: agg[k] / args.steps for k in ("ms_sample", "ms_minsum", "ms_osd", "ms_logical")},
+            "stage_ms_per_step": {**{k: agg[k] / n_stage for k in ("ms_sample", "ms_minsum", "ms_osd", "ms_logical")},
+                                  "note": "two un-pipelined single-batch steps after the timed region (stages of consecutive batches overlap inside it)"},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "logical_error_rate": float(ctot[2] / max(1, ctot[3])), "z_ler": float(ctot[0] / max(1, ctot[3])), "x_ler": float(ctot[1] / max(1, ctot[3])),
             "nonconverged_side_fraction": float(nonconv_frac),
             "edge_messages_per_s_whole_job": world * agg["edge_messages"] / (ms_max * 1e-3),
             "osd_sides_per_s": (agg["osd_sides"] / (agg["ms_osd"] * 1e-3)) if agg["ms_osd"] > 0 else None,
+            "cpu_baseline_reference": reference_cpu_timing(),
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle.cpu_baseline import CpuBaseline
