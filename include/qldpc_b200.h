@@ -40,6 +40,12 @@ typedef enum {
 #define QB_ALPHA_DYNAMIC 1   /* "dynamical": alpha_it = 1 - 2^-(it+1)  (kernels.py:272-273) */
 #define QB_ALPHA_SEQUENCE 2  /* "alvarado-autoregressive": alpha_seq[min(it, len-1)] (kernels.py:402-405) */
 
+/* arithmetic of the batched min-sum kernel.  QB_PRECISION_F32 is the default and the only mode the parity claims refer
+ * to.  QB_PRECISION_HALF2 is an explicit opt-in: two shots share every 32-bit shared-memory slot as IEEE half floats
+ * (about twice the min-sum throughput, NOT the reference's arithmetic; float32 posteriors for OSD). */
+#define QB_PRECISION_F32 0
+#define QB_PRECISION_HALF2 1
+
 typedef struct qb_decoder qb_decoder;    /* one decoding side: Tanner graph, priors, logical rows */
 typedef struct qb_sampler qb_sampler;    /* circuit fault tables: location -> column signatures */
 typedef struct qb_pipeline qb_pipeline;  /* sampler + Z decoder + X decoder + batch workspaces */
@@ -52,6 +58,7 @@ typedef struct {
     int32_t alpha_len_z, alpha_len_x;
     float clip_llr;          /* 20.0 in every engine call (sparse.py:13) */
     int32_t use_osd;         /* 1: OSD-0 on non-converged sides (engine.py:96-97); 0: keep BP output */
+    int32_t precision;       /* QB_PRECISION_F32 (0, default) or QB_PRECISION_HALF2 (explicit opt-in) */
 } qb_decode_config;
 
 const char *qb_last_error(void);
@@ -65,6 +72,10 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr_h,
                       const double *prior_h, int32_t k, const int32_t *logical_ptr_h,
                       const int32_t *logical_idx_h, qb_decoder **out);
 int qb_decoder_set_prior(qb_decoder *dec, const double *prior_h);
+/* Min-sum arithmetic used by qb_minsum_batch / qb_minsum_decode_host on this handle (QB_PRECISION_*; the pipeline takes
+ * it from qb_decode_config).  QB_PRECISION_HALF2 fails with QB_ERR_UNSUPPORTED at decode time when the graph has no
+ * per-edge plan; it never silently falls back. */
+int qb_decoder_set_precision(qb_decoder *dec, int32_t precision);
 
 /* Host-only (no CUDA call): statistics of the shared-memory layout the per-edge min-sum kernel would use for this
  * graph (csrc/edge_layout.h): one float per Tanner-graph edge, check rows in conflict-free 128-bit order, the slot of

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QLDPC_B200_LIB", os.path.join(_HERE, "libqldpc_b200.so"))   # override: instrumented builds
 
 QB_ALPHA_FIXED, QB_ALPHA_DYNAMIC, QB_ALPHA_SEQUENCE = 0, 1, 2
+QB_PRECISION_F32, QB_PRECISION_HALF2 = 0, 1
 
 _lib = None
 _lock = threading.Lock()
@@ -28,7 +29,8 @@ class QbError(RuntimeError):
 class DecodeConfig(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("alpha_mode", C.c_int32), ("alpha_z", C.c_float), ("alpha_x", C.c_float),
                 ("alpha_seq_z_h", C.c_void_p), ("alpha_seq_x_h", C.c_void_p),
-                ("alpha_len_z", C.c_int32), ("alpha_len_x", C.c_int32), ("clip_llr", C.c_float), ("use_osd", C.c_int32)]
+                ("alpha_len_z", C.c_int32), ("alpha_len_x", C.c_int32), ("clip_llr", C.c_float), ("use_osd", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 class PipelineStats(C.Structure):
@@ -44,7 +46,7 @@ EXPORTS = [
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
     "qb_pipeline_decode_host", "qb_pipeline_last_stats", "qb_pipeline_enable_detail", "qb_pipeline_last_batch_detail",
-    "qb_osd0_pipeline_host", "qb_decoder_osd_stats",
+    "qb_osd0_pipeline_host", "qb_decoder_osd_stats", "qb_decoder_set_precision",
 ]
 
 
@@ -130,6 +132,10 @@ class Decoder:
         indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
         indices = np.nonzero(mask)[1].astype(np.int32)
         return cls(indptr, indices, H.shape[1], prior, logical_rows, device)
+
+    def set_precision(self, precision):
+        """QB_PRECISION_F32 (default) or QB_PRECISION_HALF2 (packed opt-in mode) for this handle's min-sum calls."""
+        check(load().qb_decoder_set_precision(self._h, int(precision)))
 
     def set_prior(self, prior):
         prior = np.ascontiguousarray(prior, dtype=np.float64)
@@ -284,13 +290,14 @@ class Sampler:
             pass
 
 
-def make_config(max_iter, alpha_mode, alpha_z=1.0, alpha_x=1.0, clip_llr=20.0, use_osd=True):
+def make_config(max_iter, alpha_mode, alpha_z=1.0, alpha_x=1.0, clip_llr=20.0, use_osd=True, precision=QB_PRECISION_F32):
     """Build a qb_decode_config; returns (config, keepalive) -- keep both until the call returns."""
     cfg = DecodeConfig()
     keep = []
     cfg.max_iter = int(max_iter)
     cfg.clip_llr = float(clip_llr)
     cfg.use_osd = 1 if use_osd else 0
+    cfg.precision = int(precision)
     if alpha_mode == QB_ALPHA_SEQUENCE:
         sz = np.ascontiguousarray(alpha_z, dtype=np.float32)
         sx = np.ascontiguousarray(alpha_x, dtype=np.float32)

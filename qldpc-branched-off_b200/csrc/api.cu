@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "edge_dev.cuh"
 
 namespace qb {
 
@@ -207,6 +208,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     }
     std::vector<float> pf(n);
     for (int j = 0; j < n; ++j) pf[j] = (float)prior[j];
+    d->h_prior = pf;
     std::vector<uint32_t> logmask(n, 0u);
     for (int b = 0; b < k; ++b)
         for (int p = lptr[b]; p < lptr[b + 1]; ++p) {
@@ -244,6 +246,9 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     if (dec->g.n) QB_CUDA(cudaMemcpy(dec->d_prior, pf.data(), sizeof(float) * pf.size(), cudaMemcpyHostToDevice));
     // the per-edge layout groups variables by prior value: rebuild it
     QB_CUDA(cudaDeviceSynchronize());
+    dec->h_prior = pf;
+    edge_plan_h2_destroy(dec->edge_h2);
+    dec->edge_h2 = nullptr;
     edge_plan_destroy(dec->edge);
     dec->edge = nullptr;
     // same predicate as qb_decoder_create: non-finite priors or a graph that can produce NaN posteriors on its own
@@ -252,11 +257,20 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     return QB_OK;
 }
 
+int qb_decoder_set_precision(qb_decoder *dec, int32_t precision)
+{
+    QB_REQUIRE(dec != nullptr, "NULL argument");
+    QB_REQUIRE(precision == QB_PRECISION_F32 || precision == QB_PRECISION_HALF2, "unknown precision");
+    dec->precision = precision;
+    return QB_OK;
+}
+
 void qb_decoder_destroy(qb_decoder *dec)
 {
     if (!dec) return;
     cudaSetDevice(dec->device);
     for (void *p : dec->owned) cudaFree(p);
+    edge_plan_h2_destroy(dec->edge_h2);
     edge_plan_destroy(dec->edge);
     if (dec->d_alpha) cudaFree(dec->d_alpha);
     dec->scratch.release(); dec->work.release(); dec->ovf.release();
@@ -286,6 +300,7 @@ int qb_minsum_batch(qb_decoder *dec, const uint32_t *syn_bits_d, int32_t B, int3
     a.syn_bits = syn_bits_d; a.B = B; a.max_iter = max_iter; a.alpha_d = dec->d_alpha;
     a.damping = damping; a.clip = clip_llr; a.dense_variant = 0;
     a.hard_bits = hard_bits_d; a.converged = converged_d; a.final_iter = final_iter_d; a.post = post_d;
+    a.precision = dec->precision;
     return launch_minsum(dec, a, st);
 }
 
@@ -320,6 +335,7 @@ int qb_minsum_decode_host(qb_decoder *dec, const int8_t *syndrome_h, int32_t B, 
     a.syn_bits = d_syn; a.B = B; a.max_iter = max_iter; a.alpha_d = dec->d_alpha;
     a.damping = (float)damping; a.clip = (float)clip_llr; a.dense_variant = dense_variant;
     a.hard_bits = d_hard; a.converged = d_conv; a.final_iter = d_fin; a.post = d_post;
+    a.precision = dense_variant ? QB_PRECISION_F32 : dec->precision;
     if (int rc = launch_minsum(dec, a, st)) return rc;
     if (int rc = launch_unpack_bits(d_hard, B, g.n, g.nw, d_hard8, st)) return rc;
     if (g.n) QB_CUDA(cudaMemcpyAsync(hard_h, d_hard8, sB * g.n, cudaMemcpyDeviceToHost, st));
@@ -727,6 +743,7 @@ static int check_cfg(const qb_decode_config *cfg)
 {
     QB_REQUIRE(cfg != nullptr, "cfg is NULL");
     QB_REQUIRE(cfg->max_iter >= 0, "max_iter must be >= 0");
+    QB_REQUIRE(cfg->precision == QB_PRECISION_F32 || cfg->precision == QB_PRECISION_HALF2, "unknown precision");
     if (int rc = check_alpha(cfg->alpha_mode, cfg->alpha_z, cfg->alpha_seq_z_h, cfg->alpha_len_z)) return rc;
     if (int rc = check_alpha(cfg->alpha_mode, cfg->alpha_x, cfg->alpha_seq_x_h, cfg->alpha_len_x)) return rc;
     return QB_OK;
@@ -779,6 +796,7 @@ static int decode_batch(qb_pipeline *p, qb_workspace &W, qb_workspace &other, in
         a.hard_bits = side ? W.hardX : W.hardZ; a.converged = side ? W.convX : W.convZ;
         a.final_iter = side ? W.itX : W.itZ; a.post = side ? W.postX : W.postZ; a.post_failed_only = 1;
         a.fail_count = W.nfail + side; a.fail_idx = side ? W.failX : W.failZ; a.fail_wt = side ? W.fwX : W.fwZ;
+        a.precision = cfg->precision;
         if (int rc = launch_minsum(d, a, st)) return rc;
         p->stats.kernel_launches++;
     }

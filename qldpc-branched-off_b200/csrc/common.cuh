@@ -68,6 +68,7 @@ struct GraphDev {
 };
 
 struct EdgePlan;   // per-edge min-sum kernel: layout + device tables (minsum_edge.cu)
+struct EdgePlanH2; // its packed half2 companion (minsum_edge_h2.cu)
 }  // namespace qb
 
 struct qb_decoder {
@@ -87,6 +88,9 @@ struct qb_decoder {
     int sm_count = 148;
     int max_smem_optin = 0;
     qb::EdgePlan *edge = nullptr;   // nullptr: graph does not fit the per-edge kernel
+    qb::EdgePlanH2 *edge_h2 = nullptr;   // packed mode, built on first use
+    std::vector<float> h_prior;     // float priors as the kernels see them
+    int precision = 0;              // QB_PRECISION_* used by the host-buffer entry points (qb_decoder_set_precision)
 };
 
 struct qb_sampler {
@@ -120,6 +124,7 @@ struct MinsumLaunch {
     int32_t *fail_count;        // nullable: device counter, non-converged shots are appended
     int32_t *fail_idx;
     int32_t *fail_wt;           // nullable: residual syndrome weight of each appended shot (OSD scheduling hint)
+    int precision;              // QB_PRECISION_F32 (default) / QB_PRECISION_HALF2 (packed mode, opt-in)
 };
 int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st);
 int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out);

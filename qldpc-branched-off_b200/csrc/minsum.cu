@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "edge_dev.cuh"
 
 namespace qb {
 
@@ -681,6 +682,13 @@ static int launch_fast(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
 int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
 {
     if (a.B <= 0) return QB_OK;
+    if (a.precision == QB_PRECISION_HALF2) {
+        // opt-in packed mode: only on the per-edge plan (damping 1, uniform priors per slice); no silent downgrade
+        if (!(a.damping == 1.0f && dec->edge && a.max_iter > 0)) { set_error("packed half2 min-sum needs the per-edge plan (damping = 1, max_iter > 0, graph fits one SM)"); return QB_ERR_UNSUPPORTED; }
+        if (!dec->edge_h2) if (int rc = edge_plan_h2_create(dec->edge, dec->g.nw, dec->h_prior.data(), &dec->edge_h2)) return rc;
+        if (!edge_h2_fits(dec, dec->edge, dec->edge_h2)) { set_error("packed half2 min-sum: plan does not fit (shared memory / per-lane priors)"); return QB_ERR_UNSUPPORTED; }
+        return launch_minsum_edge_h2(dec, dec->edge, dec->edge_h2, a, st);
+    }
     if (a.damping == 1.0f && dec->edge && a.max_iter > 0) return launch_minsum_edge(dec, dec->edge, a, st);
     const int S = (a.damping == 1.0f) ? fast_shots_per_cta(dec) : 0;
     if (S == 4) return launch_fast<4>(dec, a, st);

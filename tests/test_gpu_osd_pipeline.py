@@ -47,17 +47,17 @@ def _reference_stream_events(cc, B, p, base_seed=1234, first=0):
     return np.array(ev_ptr, dtype=np.int32), (np.concatenate(evs) if evs else np.zeros(0, np.uint32)).astype(np.uint32)
 
 
-def _check_pipeline_osd(tag, p, max_iter, B, seed):
+def _check_pipeline_osd(tag, p, max_iter, B, seed, precision=_lib.QB_PRECISION_F32):
     """Run B host-sampled shots through the pipeline and compare every non-converged side with the oracle."""
     from qldpc_b200.simulation.engine import ShotEngine
     s = code_setup(tag); M = matrices(tag, p)
     eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=B)
     eng.pipeline.enable_detail(True)
     ev_ptr, ev = _host_events(s["ft"], B, p, seed)
-    cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC)
+    cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC, precision=precision)
     counts, flags, conv, fin = eng.pipeline.run_events(ev_ptr, ev, cfg, want_detail=True)
     sz, tz, sx, tx = eng.sampler.syndromes_from_events(ev_ptr, ev)
-    out = dict(sides=0, paths={1: 0, 2: 0}, pivots=[], mismatches=[])
+    out = dict(sides=0, paths={1: 0, 2: 0}, pivots=[], mismatches=[], conv=conv, fin=fin, flags=flags, counts=counts)
     for side, H, syn in ((0, M["HdecZ"], sz), (1, M["HdecX"], sx)):
         H = np.asarray(H) & 1; m, n = H.shape
         col_ptr, row_idx = orc._csc(H)
