@@ -152,7 +152,7 @@ __device__ __forceinline__ void row_dispatch_h2(uint32_t *E, const uint4 *E0, in
 // ---- variables -----------------------------------------------------------------------------------------------------
 struct ColCtxH2 {
     uint32_t ix, lane4, lane8, sg;
-    uint32_t fpA, fpB;          // XOR of the fingerprints of the variables whose hard decision is 1, per shot
+    uint32_t fp2;               // XOR of the fingerprints of the variables whose hard decision is 1: shot A low half, shot B high half
     uint32_t hwA, hwB;          // lane j keeps the hard-decision words of the warp's j-th task
     uint32_t t4, lane_t4;
     int lane;
@@ -194,24 +194,22 @@ __device__ __forceinline__ void col_task_h2(ColCtxH2 &c, const EdgePriors &pri, 
         if constexpr (EXACT) q &= ~h2_nan_mask(q);                               // kernels.py:328-329
         sts_u32(addr[k], q);
     }
-    bool negA, negB;
+    uint32_t lt;                                                                  // 0xFFFF per half whose hard decision is 1
     if constexpr (WRITE_V) {
         float2 s = D > 0 ? h2_to_f2(r[0]) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 1; k < D; ++k) { const float2 x = h2_to_f2(r[k]); s.x += x.x; s.y += x.y; }
         const float pf = __uint_as_float(*reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pri.bits) + c.t4));
         s.x += pf; s.y += pf;
-        negA = s.x < 0.f; negB = s.y < 0.f;
+        lt = (s.x < 0.f ? 0xFFFFu : 0u) | (s.y < 0.f ? 0xFFFF0000u : 0u);
         const uint32_t vid = __ldg(c.vid);
         if (vid != 0xFFFFu) { if (c.postA) c.postA[vid] = s.x; if (c.postB) c.postB[vid] = s.y; }
     } else {
-        const uint32_t lt = h2_lt_mask(v, 0u);
-        negA = (lt & 0xFFFFu) != 0u; negB = (lt >> 16) != 0u;
+        lt = h2_lt_mask(v, 0u);
     }
     const uint32_t sig = lds_u8(c.sg);
-    if (negA) c.fpA ^= sig;
-    if (negB) c.fpB ^= sig;
-    const uint32_t ha = __ballot_sync(0xFFFFFFFFu, negA), hb = __ballot_sync(0xFFFFFFFFu, negB);
+    c.fp2 ^= __byte_perm(sig, 0u, 0x4040) & lt;                                   // sig in both halves
+    const uint32_t ha = __ballot_sync(0xFFFFFFFFu, (lt & 0xFFFFu) != 0u), hb = __ballot_sync(0xFFFFFFFFu, (lt >> 16) != 0u);
     if (c.lane_t4 == c.t4) { c.hwA = ha; c.hwB = hb; }
     c.vid += 32;
     c.ix += ((D + 1) / 2) * 128; c.sg += 32; c.t4 += 4;
@@ -252,8 +250,8 @@ __device__ __forceinline__ void col_task_generic_h2(ColCtxH2 &c, uint32_t meta, 
             negA = (lt & 0xFFFFu) != 0u; negB = (lt >> 16) != 0u;
         }
         const uint32_t sig = lds_u8(c.sg);
-        if (negA) c.fpA ^= sig;
-        if (negB) c.fpB ^= sig;
+        if (negA) c.fp2 ^= sig;
+        if (negB) c.fp2 ^= sig << 16;
     }
     const uint32_t ha = __ballot_sync(0xFFFFFFFFu, negA), hb = __ballot_sync(0xFFFFFFFFu, negB);
     if (c.lane_t4 == c.t4) { c.hwA = ha; c.hwB = hb; }
@@ -294,6 +292,42 @@ __device__ __forceinline__ void phase_b_h2(ColCtxH2 &c, uint4 cls, int t_end, co
         col_task_generic_h2<WRITE_V>(c, cmeta[c.t4 >> 2], lane_prior ? lane_prior + (c.t4 >> 2) * 32 + c.lane : nullptr, pri);
 }
 
+// write out one shot of the pair: hard decision to natural order, flags, failure queue (uniform call: contains barriers)
+template <int THREADS>
+__device__ __forceinline__ void finish_shot_h2(const EdgeDev &eg, const MinsumLaunch &a, const uint32_t *hperm, const uint32_t *syn,
+                                               uint32_t *par, uint32_t *hnat, const uint32_t *cmeta, uint16_t *s_plist, int *s_pcount,
+                                               int *s_wt, int shot, bool converged, int it_fin, int tid, int warp, int lane)
+{
+    const bool need_wt = !converged && a.max_iter > 0 && a.fail_wt != nullptr;
+    for (int w = tid; w < eg.nw; w += THREADS) hnat[w] = 0u;
+    __syncthreads();
+    for (int t = tid; t < eg.n_csl; t += THREADS) {
+        uint32_t bits = hperm[t];
+        while (bits) {
+            const int b = __ffs(bits) - 1; bits &= bits - 1;
+            const uint32_t vid = eg.var_id[t * 32 + b];
+            atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
+        }
+    }
+    if (need_wt) {
+        parity_of_hard(eg, hperm, cmeta, par, s_plist, s_pcount, tid, THREADS);
+        __syncthreads();
+        if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) *s_wt = w; }
+    }
+    __syncthreads();
+    for (int w = tid; w < eg.nw; w += THREADS) a.hard_bits[(size_t)shot * eg.nw + w] = hnat[w];
+    if (tid == 0) {
+        a.converged[shot] = converged ? 1 : 0;
+        a.final_iter[shot] = it_fin;
+        if (!converged && a.fail_count) {
+            const int slot = atomicAdd(a.fail_count, 1);
+            a.fail_idx[slot] = shot;
+            if (a.fail_wt) a.fail_wt[slot] = need_wt ? *s_wt : 0;
+        }
+    }
+    __syncthreads();
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------------
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -315,7 +349,7 @@ minsum_edge_h2_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant_
     __shared__ int s_wt, s_next, s_pcount;
     __shared__ uint16_t s_plist[PAR_LIST_CAP];
     __shared__ uint32_t s_alpha2[128];
-    __shared__ uint32_t s_fp[2][2], s_target[2];
+    __shared__ uint32_t s_fp[2], s_target[2];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_min_sync(0xFFFFFFFFu, tid >> 5);
@@ -339,15 +373,16 @@ minsum_edge_h2_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant_
     const uint32_t clip2 = f_to_h2(a.clip);
 
     while (pair < n_pairs) {
-        const int shot[2] = {2 * pair, 2 * pair + 1};
-        const bool present[2] = {true, shot[1] < a.B};
+        const int shotA = 2 * pair, shotB = 2 * pair + 1;
+        const bool presentB = shotB < a.B;
         // ---- load both syndromes (permuted) and their fingerprints ----
         for (int t = warp; t < eg.n_rsl; t += THREADS / 32) {
             const uint32_t rid = eg.row_id[t * 32 + lane];
             const uint32_t msk = eg.row_mask[t * 32 + lane] & 0xFFu;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const bool bit = present[s] && rid != 0xFFFFu && ((a.syn_bits[(size_t)shot[s] * eg.mw + (rid >> 5)] >> (rid & 31)) & 1u);
+                const int sh = s ? shotB : shotA;
+                const bool bit = (s == 0 || presentB) && rid != 0xFFFFu && ((a.syn_bits[(size_t)sh * eg.mw + (rid >> 5)] >> (rid & 31)) & 1u);
                 const uint32_t tg = __reduce_xor_sync(0xFFFFFFFFu, bit ? msk : 0u);
                 const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
                 if (lane == 0) { (s ? synB : synA)[t] = word; if (tg) atomicXor(&s_target[s], tg); }
@@ -356,45 +391,8 @@ minsum_edge_h2_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant_
         }
         __syncthreads();
         if (tid == 0) s_next = atomicAdd(pair_counter, 1);
-        const uint32_t target[2] = {s_target[0], s_target[1]};
-        bool done[2] = {false, !present[1]};
-        bool conv[2] = {false, false};
-        int fin[2] = {a.max_iter - 1, a.max_iter - 1};
-
-        // write out one shot: hard decision to natural order, flags, failure queue (uniform call: contains barriers)
-        auto finish = [&](int s, bool converged, int it_fin) {
-            const uint32_t *hperm = s ? hpermB : hpermA;
-            const uint32_t *syn = s ? synB : synA;
-            const bool need_wt = !converged && a.max_iter > 0 && a.fail_wt != nullptr;
-            for (int w = tid; w < eg.nw; w += THREADS) hnat[w] = 0u;
-            __syncthreads();
-            for (int t = tid; t < eg.n_csl; t += THREADS) {
-                uint32_t bits = hperm[t];
-                while (bits) {
-                    const int b = __ffs(bits) - 1; bits &= bits - 1;
-                    const uint32_t vid = eg.var_id[t * 32 + b];
-                    atomicOr(&hnat[vid >> 5], 1u << (vid & 31));
-                }
-            }
-            if (need_wt) {
-                parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
-                __syncthreads();
-                if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
-            }
-            __syncthreads();
-            for (int w = tid; w < eg.nw; w += THREADS) a.hard_bits[(size_t)shot[s] * eg.nw + w] = hnat[w];
-            if (tid == 0) {
-                a.converged[shot[s]] = converged ? 1 : 0;
-                a.final_iter[shot[s]] = it_fin;
-                if (!converged && a.fail_count) {
-                    const int slot = atomicAdd(a.fail_count, 1);
-                    a.fail_idx[slot] = shot[s];
-                    if (a.fail_wt) a.fail_wt[slot] = need_wt ? s_wt : 0;
-                }
-            }
-            __syncthreads();
-        };
-
+        const uint32_t targetA = s_target[0], targetB = s_target[1];
+        bool doneA = false, doneB = !presentB;
         for (int it = 0; it < a.max_iter; ++it) {
             const uint32_t alpha2 = it < 128 ? s_alpha2[it] : f_to_h2(a.alpha_d[it]);
             for (int t = r0; t < r1; ++t) {
@@ -406,36 +404,48 @@ minsum_edge_h2_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant_
                 if (it == 0) row_dispatch_h2<true>(E, E0h, (int)(d.x >> 2), stride, lane, K, synsign2, alpha2, H2_INF, pads);
                 else row_dispatch_h2<false>(E, E0h, (int)(d.x >> 2), stride, lane, K, synsign2, alpha2, clip2, pads);
             }
-            if (tid == 0) { s_fp[it & 1][0] = 0u; s_fp[it & 1][1] = 0u; }
+            if (tid == 0) s_fp[it & 1] = 0u;
             __syncthreads();
             const bool write_v = a.post && (api || it == a.max_iter - 1);
             ColCtxH2 c;
             c.ix = ix0; c.lane4 = lane * 4; c.lane8 = lane * 8;
             c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
-            c.fpA = 0u; c.fpB = 0u; c.hwA = 0u; c.hwB = 0u;
+            c.fp2 = 0u; c.hwA = 0u; c.hwB = 0u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
-            c.postA = (a.post && !done[0]) ? a.post + (size_t)shot[0] * eg.n : nullptr;
-            c.postB = (a.post && !done[1]) ? a.post + (size_t)shot[1] * eg.n : nullptr;
+            c.postA = (a.post && !doneA) ? a.post + (size_t)shotA * eg.n : nullptr;
+            c.postB = (a.post && !doneB) ? a.post + (size_t)shotB * eg.n : nullptr;
             if (write_v) phase_b_h2<true>(c, cls, c1, cmeta, eg.lane_prior, pri, pri_h2);
             else phase_b_h2<false>(c, cls, c1, cmeta, eg.lane_prior, pri, pri_h2);
-            if (lane < c1 - c0) { if (!done[0]) hpermA[c0 + lane] = c.hwA; if (!done[1]) hpermB[c0 + lane] = c.hwB; }
-            const uint32_t fa = __reduce_xor_sync(0xFFFFFFFFu, c.fpA), fb = __reduce_xor_sync(0xFFFFFFFFu, c.fpB);
-            if (lane == 0) { if (fa) atomicXor(&s_fp[it & 1][0], fa); if (fb) atomicXor(&s_fp[it & 1][1], fb); }
+            if (lane < c1 - c0) { if (!doneA) hpermA[c0 + lane] = c.hwA; if (!doneB) hpermB[c0 + lane] = c.hwB; }
+            const uint32_t f2 = __reduce_xor_sync(0xFFFFFFFFu, c.fp2);
+            if (lane == 0 && f2) atomicXor(&s_fp[it & 1], f2);
             __syncthreads();
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (done[s] || s_fp[it & 1][s] != target[s]) continue;                // uniform
-                parity_of_hard(eg, s ? hpermB : hpermA, cmeta, par, s_plist, &s_pcount, tid, THREADS);
+            const uint32_t fpw = s_fp[it & 1];
+            if (!doneA && (fpw & 0xFFFFu) == targetA) {                                   // uniform
+                parity_of_hard(eg, hpermA, cmeta, par, s_plist, &s_pcount, tid, THREADS);
                 __syncthreads();
-                if (warp == 0) { const int w = residual_weight(par, s ? synB : synA, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
+                if (warp == 0) { const int w = residual_weight(par, synA, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
                 __syncthreads();
-                if (s_wt == 0) { conv[s] = true; fin[s] = it; done[s] = true; finish(s, true, it); }   // kernels.py:352-364
+                if (s_wt == 0) {                                                          // kernels.py:352-364
+                    doneA = true;
+                    finish_shot_h2<THREADS>(eg, a, hpermA, synA, par, hnat, cmeta, s_plist, &s_pcount, &s_wt, shotA, true, it, tid, warp, lane);
+                }
             }
-            if (done[0] && done[1]) break;
+            if (!doneB && (fpw >> 16) == targetB) {
+                parity_of_hard(eg, hpermB, cmeta, par, s_plist, &s_pcount, tid, THREADS);
+                __syncthreads();
+                if (warp == 0) { const int w = residual_weight(par, synB, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
+                __syncthreads();
+                if (s_wt == 0) {
+                    doneB = true;
+                    finish_shot_h2<THREADS>(eg, a, hpermB, synB, par, hnat, cmeta, s_plist, &s_pcount, &s_wt, shotB, true, it, tid, warp, lane);
+                }
+            }
+            if (doneA && doneB) break;
         }
-#pragma unroll
-        for (int s = 0; s < 2; ++s) if (!done[s]) finish(s, false, a.max_iter - 1);
+        if (!doneA) finish_shot_h2<THREADS>(eg, a, hpermA, synA, par, hnat, cmeta, s_plist, &s_pcount, &s_wt, shotA, false, a.max_iter - 1, tid, warp, lane);
+        if (!doneB) finish_shot_h2<THREADS>(eg, a, hpermB, synB, par, hnat, cmeta, s_plist, &s_pcount, &s_wt, shotB, false, a.max_iter - 1, tid, warp, lane);
         if (tid == 0) { s_target[0] = 0u; s_target[1] = 0u; }
         pair = s_next;
         __syncthreads();
