@@ -40,6 +40,7 @@ constexpr int SELF_THREADS = 256;
 constexpr int SELF_BINS = 2048;            // 64 per octave over 2^-25 .. 2^7, clamped (monotone in the key)
 constexpr int SELF_SHIFT = 17;
 constexpr int SELF_BASE = (127 - 25) << 6;
+constexpr int FREE_WARPS_MAX = 8;          // upper bound of sides per CTA (launch bound)
 constexpr int FREE_WARPS = 4;              // independent sides per CTA of the elimination kernel (fewer when a side's state is large)
 
 // counters[]: 0 select queue, 1 tier-A queue, 2 tier-B queue, 3 tier-A overflow count (= tier-B input), 4 tier-B overflow
@@ -52,7 +53,7 @@ struct OsdFreeArgs {
     OsdLaunch a;
     int F;                       // queue length bound (n_fail_d gives the exact count when set)
     int cap;                     // candidates materialised per side at most (= stride of cand)
-    int cap_per_wt;              // a side of residual weight wt gets the next power of two >= cap_per_wt * wt (512 .. cap)
+    int cap_per_wt;              // a side of residual weight wt gets cap_per_wt * wt candidates (256 .. cap, multiple of 64)
     int max_wt;                  // heavier residuals are not materialised (more free rows than any tier has slots)
     uint16_t *cand;              // [F][cap] column ids, ascending (|posterior|, index)
     int32_t *ncand;              // [F] candidates materialised; -1: hand the side to the full-width kernel
@@ -156,10 +157,11 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         if (lane == 31) s_wsum[warp] = (int)inc;
         __syncthreads();
         const int wt_side = s_wt;
-        int cap_side = 512;
-        while (cap_side < P.cap && cap_side < P.cap_per_wt * wt_side) cap_side <<= 1;
-        cap_side = second ? P.cap : min(cap_side, P.cap);
-        const int sel_min = second ? cap_side : cap_side - (cap_side >> 3);     // second pass: every column
+        // first pass: cap_per_wt candidates per unit of residual weight (measured on the gross code: sides of weight
+        // 20-40 examine <= 592 candidates in 99 % of the cases, 60-80: <= 1061, 100+: <= 3015), closed 64 below the cap
+        int cap_side = min(P.cap, max(256, (P.cap_per_wt * wt_side + 63) & ~63));
+        if (second) cap_side = P.cap;
+        const int sel_min = second ? cap_side : cap_side - 64;                  // second pass: every column
         uint32_t run = inc - local;
         for (int w = 0; w < warp; ++w) run += (uint32_t)s_wsum[w];
         int b1 = SELF_BINS - 1, b2 = -1;                       // first bin reaching sel_min / last bin within the cap
@@ -235,7 +237,7 @@ __host__ __device__ inline size_t free_per_warp_bytes(int m, int rcap, int Q)
 // signature; lanes 0 .. 4Q-1 additionally own word `lane` of the transformed syndrome (sl) and of the slot-in-use mask (ul).
 // (Q = 3: 384 slots, 12 words per vector in a 16-lane group)
 template <int Q>
-__global__ void __launch_bounds__(FREE_WARPS * 32) osd_free_kernel(const __grid_constant__ OsdFreeArgs P, const __grid_constant__ OsdFreeTier Tr)
+__global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __grid_constant__ OsdFreeArgs P, const __grid_constant__ OsdFreeTier Tr)
 {
     constexpr int WV = 4 * Q;                 // words per vector
     constexpr int LV = Q == 1 ? 4 : (Q == 2 ? 8 : 16);   // lanes per vector in the gather layout (power of two >= WV)
@@ -500,13 +502,18 @@ static bool free_plan(const qb_decoder *dec, FreePlan &pl)
     if (getenv("QLDPC_B200_OSD_FULLWIDTH")) return false;
     const bool big = g.m > 1536;
     int rcapA = big ? 2048 : 512, rcapB = big ? 3072 : 1024;
-    if (const char *e = getenv("QLDPC_B200_OSD_RCAP")) { const int v = atoi(e); if (v >= 128 && v <= 4096) { rcapA = v; rcapB = 2 * v; } }
+    if (const char *e = getenv("QLDPC_B200_OSD_RCAP")) { const int v = atoi(e); if (v >= 64 && v <= 4096) { rcapA = v; rcapB = 2 * v; } }
+    if (const char *e = getenv("QLDPC_B200_OSD_RCAP_B")) { const int v = atoi(e); if (v >= 64 && v <= 8192) rcapB = v; }
     pl.cap = big ? 8192 : 2048;
     if (const char *e = getenv("QLDPC_B200_OSD_CAP")) { const int v = atoi(e); if (v >= 64 && v <= 16384) pl.cap = v & ~31; }
     pl.cap = std::max(32, std::min(pl.cap, (g.n + 31) & ~31));
-    pl.cap_per_wt = 28;
-    if (!tier_plan(dec, big ? 2 : 1, rcapA, FREE_WARPS, pl.A)) return false;
-    if (!tier_plan(dec, big ? 3 : 2, rcapB, FREE_WARPS, pl.B)) return false;
+    pl.cap_per_wt = 32;
+    if (const char *e = getenv("QLDPC_B200_OSD_CAP_PER_WT")) { const int v = atoi(e); if (v >= 1 && v <= 256) pl.cap_per_wt = v; }
+    int warpsA = FREE_WARPS, warpsB = 6;
+    if (const char *e = getenv("QLDPC_B200_OSD_WARPS_A")) { const int v = atoi(e); if (v >= 1 && v <= FREE_WARPS_MAX) warpsA = v; }
+    if (const char *e = getenv("QLDPC_B200_OSD_WARPS_B")) { const int v = atoi(e); if (v >= 1 && v <= FREE_WARPS_MAX) warpsB = v; }
+    if (!tier_plan(dec, big ? 2 : 1, rcapA, warpsA, pl.A)) return false;
+    if (!tier_plan(dec, big ? 3 : 2, rcapB, warpsB, pl.B)) return false;
     pl.max_wt = 128 * pl.B.Q;
     pl.cap2 = (g.n + 31) & ~31;                                              // second pass: all columns
     pl.smem_sel = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap * (4 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
