@@ -31,7 +31,7 @@ for name, p, max_iter, shots in CONFIGS:
     M = matrices_from_tables(ft, p, d)
     batch = min(65536, shots) if name != "[[288, 12, 18]]" else 8192
     eng = ShotEngine(cc, code["Lx"], code["Lz"], M, max_batch=batch)
-    cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC)
+    cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC, precision=int(os.environ.get("QB_PRECISION", "0")))
     eng.pipeline.run(1, 0, batch, p, cfg)
     counts, _ = eng.pipeline.run(1234, 0, shots, p, cfg)
     st = eng.pipeline.stats()
@@ -40,6 +40,7 @@ for name, p, max_iter, shots in CONFIGS:
                nonconverged_side_frac=round((counts[4] + counts[5]) / (2 * counts[3]), 4),
                edge_messages_per_s=round(st["edge_messages"] / (st["ms_minsum"] * 1e-3) / 1e9, 1),
                ms=dict(minsum=round(st["ms_minsum"], 1), osd=round(st["ms_osd"], 1), sample=round(st["ms_sample"], 1)),
-               table_build_s=round(tb, 2))
+               table_build_s=round(tb, 2), osd_tier_exits=dict(z=eng.decZ.osd_stats(), x=eng.decX.osd_stats()),
+               precision="half2" if os.environ.get("QB_PRECISION", "0") == "1" else "f32")
     print(json.dumps(row), flush=True)
     eng.close()
