@@ -193,14 +193,22 @@ int qb_syndrome_from_events(qb_sampler *s, const int32_t *ev_ptr_d, const uint32
 int qb_syndrome_from_events_host(qb_sampler *s, const int32_t *ev_ptr_h, const uint32_t *events_h, int32_t B,
                                  int8_t *sparseZ_h, int8_t *trueZ_h, int8_t *sparseX_h, int8_t *trueX_h);
 
-/* K1+K2 fused: Philox4x32-10 keyed by `seed`, counter = global shot index, one independent
- * Bernoulli(p) draw per location and a uniform Pauli outcome (the noise model of
- * src/noise/kernels.py:176-353; a different generator than the reference's per-shot MT19937
- * reseed, engine.py:70, validated statistically).  Shots first_shot .. first_shot+B-1.
- * nfaults_d (nullable, [B]) receives the number of faults drawn per shot. */
+/* K1+K2 fused: Philox4x32-10 keyed by `seed`, counter = (global shot index, lane + 32 * call, 2).  Every location fails
+ * independently with probability p and gets a uniform Pauli outcome (the noise model of src/noise/kernels.py:176-353; a
+ * different generator than the reference's per-shot MT19937 reseed, engine.py:70, validated statistically).  The faults
+ * of a shot are placed by sampling the geometric gaps between them: lane l of the shot's warp owns locations
+ * [l*C, (l+1)*C), C = ceil(L/32), and consumes its Philox words in order -- one per jump (inversion against
+ * T[k] = floor(2^32 (1-p)^k); a word below T[1023] extends the jump by another word), one per IDLE / CNOT fault for the
+ * outcome floor(word * K / 2^32), K = 3 / 15.  Shots first_shot .. first_shot+B-1; results do not depend on B or on the
+ * number of GPUs.  nfaults_d (nullable, [B]) receives the number of faults drawn per shot. */
 int qb_sample_syndromes(qb_sampler *s, uint64_t seed, uint64_t first_shot, int32_t B, double p,
                         uint32_t *synZ_bits_d, uint32_t *trueZ_d, uint32_t *synX_bits_d, uint32_t *trueX_d,
                         int32_t *nfaults_d, void *stream);
+
+/* The jump table qb_sample_syndromes uses for error rate p: table_h[k] = floor(2^32 (1-p)^k), k = 1..1023 (entry 0
+ * unused); returns the number of words written (1024) or a negative status.  Host-only; lets a test re-derive a shot's
+ * fault stream word for word. */
+int qb_sampler_geometric_table(double p, uint32_t *table_h, int32_t capacity);
 
 /* ---- fused per-shot pipeline ----------------------------------------------------------------- */
 /* _run_single_trial_fast for a range of shots (src/simulation/engine.py:68-122): sample, syndromes,

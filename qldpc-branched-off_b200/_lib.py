@@ -47,6 +47,7 @@ EXPORTS = [
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
     "qb_pipeline_decode_host", "qb_pipeline_last_stats", "qb_pipeline_enable_detail", "qb_pipeline_last_batch_detail",
     "qb_osd0_pipeline_host", "qb_decoder_osd_stats", "qb_decoder_set_precision",
+    "qb_sampler_geometric_table",
 ]
 
 
@@ -288,6 +289,15 @@ class Sampler:
             self.close()
         except Exception:
             pass
+
+
+def geometric_table(p):
+    """Jump table of the fault sampler for error rate p (uint32 [1024], entry 0 unused): qb_sampler_geometric_table."""
+    out = np.zeros(1024, dtype=np.uint32)
+    n = load().qb_sampler_geometric_table(c_double(float(p)), ptr(out), 1024)
+    if n < 0:
+        check(n)
+    return out
 
 
 def make_config(max_iter, alpha_mode, alpha_z=1.0, alpha_x=1.0, clip_llr=20.0, use_osd=True, precision=QB_PRECISION_F32):

@@ -680,6 +680,16 @@ int qb_syndrome_from_events_host(qb_sampler *s, const int32_t *ev_ptr_h, const u
     return QB_OK;
 }
 
+int qb_sampler_geometric_table(double p, uint32_t *table_h, int32_t capacity)
+{
+    QB_REQUIRE(table_h != nullptr && p > 0.0 && p < 1.0, "bad argument");
+    std::vector<uint32_t> T;
+    geometric_table(p, T);
+    QB_REQUIRE(capacity >= (int)T.size(), "table capacity too small (qb_sampler_geometric_table needs 1024 words)");
+    memcpy(table_h, T.data(), sizeof(uint32_t) * T.size());
+    return (int)T.size();
+}
+
 int qb_sample_syndromes(qb_sampler *s, uint64_t seed, uint64_t first_shot, int32_t B, double p,
                         uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX, int32_t *nfaults_d, void *stream)
 {

@@ -102,6 +102,9 @@ struct qb_sampler {
     // column signatures: 8 x uint16 per column: up to 7 rows (0xFFFF = none) ... or CSC when wider
     int32_t *d_cpZ = nullptr, *d_rowZ = nullptr, *d_cpX = nullptr, *d_rowX = nullptr;
     uint32_t *d_lmZ = nullptr, *d_lmX = nullptr;
+    uint32_t *d_geo = nullptr;          // jump table of the fault sampler for error rate geo_p (sampler.cu)
+    std::vector<uint32_t> h_geo;
+    double geo_p = -1.0;
     std::vector<void *> owned;
     qb::Scratch scratch;
     int sm_count = 148;
@@ -161,6 +164,9 @@ int launch_events_syndrome(qb_sampler *s, const int32_t *ev_ptr_d, const uint32_
 int launch_sample_syndrome(qb_sampler *s, uint64_t seed, uint64_t first_shot, int B, double p,
                            uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX,
                            int32_t *nfaults, cudaStream_t st);
+
+void geometric_table(double p, std::vector<uint32_t> &T);
+int geometric_table_size();
 
 // bit packing helpers (device kernels, utils.cu)
 int launch_pack_bits(const int8_t *src, int B, int len, uint32_t *dst, int words, cudaStream_t st);

@@ -7,6 +7,11 @@
 // signatures of its faults; the signatures are exactly the columns of the decoding matrices
 // (src/noise/builder.py:115-124).  One warp owns one shot; syndromes live in shared memory as
 // bit-packed words and faults XOR their <= 6 rows in with shared-memory atomics.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace qb {
@@ -60,6 +65,7 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 }
 
 constexpr int SAMP_WARPS = 8;
+constexpr int GEO_LOG = 10, GEO_K = (1 << GEO_LOG) - 1;     // jump table entries 1 .. GEO_K (binary search of GEO_LOG steps)
 
 // K2: explicit events
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
@@ -100,18 +106,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
     return c;
 }
 
-// K1+K2 fused.  Stream layout (documented in DESIGN.md): key = seed; counter = (shot_lo, shot_hi, q, s)
-// with s = 0: words 4q..4q+3 decide locations 4q..4q+3 (fault iff word < floor(p * 2^32));
-//      s = 1: word 0 of block q = loc picks the Pauli outcome, floor(word * K / 2^32), K = 3 or 15.
+// K1+K2 fused.  Faults are placed by sampling the GAPS between them instead of one Bernoulli draw per location (17 280
+// draws for ~86 faults per gross-code shot): lane l of the shot's warp owns the locations [l*C, (l+1)*C), C = ceil(L/32), and
+// walks them with geometric jumps, so that the 32 lanes apply their faults in lock step (~2.7 faults per lane at p = 0.005).
+//   G ~ Geometric(p), P(G >= k) = (1-p)^k, exactly by inversion on a 32-bit word r against the table
+//   T[k] = floor(2^32 (1-p)^k), k = 1..GEO_K:  G = #{k : r < T[k]};  r < T[GEO_K] means "at least GEO_K": the jump is extended
+//   by another draw (memorylessness), so the distribution has no truncation error.  The table is built on the host
+//   (qb_sampler_geometric_table returns the very words the kernel uses, for re-deriving a stream in the tests).
+// Stream layout: Philox4x32-10, key = seed, counter = (shot_lo, shot_hi, lane + 32 * call, 2) for the call-th block of four
+// words of a lane; a lane consumes its words in order: one per jump (more when extended), then, for a fault on an IDLE /
+// CNOT location, one for the Pauli outcome floor(word * K / 2^32), K = 3 or 15 (src/noise/kernels.py:262-342).
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
-sample_syndrome_kernel(SamplerDev s, uint64_t seed, uint64_t first_shot, int B, uint32_t thr,
+sample_syndrome_kernel(SamplerDev s, uint64_t seed, uint64_t first_shot, int B, const uint32_t *geo,
                        uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX, int32_t *nfaults)
 {
     extern __shared__ uint32_t sm[];
+    uint32_t *T = sm;                                                  // [GEO_K + 1], T[0] unused
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *sZ = sm + warp * (s.mwZ + s.mwX), *sX = sZ + s.mwZ;
+    uint32_t *sZ = sm + (GEO_K + 1) + warp * (s.mwZ + s.mwX), *sX = sZ + s.mwZ;
+    for (int i = threadIdx.x; i <= GEO_K; i += blockDim.x) T[i] = geo ? geo[i] : 0u;
+    __syncthreads();
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const int nblk = (s.L + 3) >> 2;
+    const int C = (s.L + 31) >> 5;
+    const int lo = min(s.L, lane * C), hi = min(s.L, lo + C);
     for (int b = blockIdx.x * SAMP_WARPS + warp; b < B; b += gridDim.x * SAMP_WARPS) {
         const uint64_t shot = first_shot + (uint64_t)b;
         const uint32_t slo = (uint32_t)shot, shi = (uint32_t)(shot >> 32);
@@ -119,23 +136,33 @@ sample_syndrome_kernel(SamplerDev s, uint64_t seed, uint64_t first_shot, int B, 
         __syncwarp();
         uint32_t tz = 0u, tx = 0u;
         int nf = 0;
-        for (int q = lane; q < nblk; q += 32) {
-            const uint4 r = philox4x32_10(make_uint4(slo, shi, (uint32_t)q, 0u), key);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        uint4 buf = make_uint4(0u, 0u, 0u, 0u);
+        int have = 0;
+        uint32_t call = 0u;
+        auto next_word = [&]() -> uint32_t {
+            if (have == 0) { buf = philox4x32_10(make_uint4(slo, shi, (uint32_t)lane + 32u * call, 2u), key); ++call; have = 4; }
+            const uint32_t r = buf.x;
+            buf.x = buf.y; buf.y = buf.z; buf.z = buf.w; --have;
+            return r;
+        };
+        int pos = lo;
+        while (geo != nullptr) {
+            // jump: number of fault-free locations before the next fault
+            while (true) {
+                const uint32_t r = next_word();
+                int a = 0, c = GEO_K;                                  // largest k in [0, GEO_K] with r < T[k]  (T[0] = 2^32)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int loc = q * 4 + i;
-                if (rr[i] < thr && loc < s.L) {
-                    int outcome = 0;
-                    const int kind = s.kind[loc];
-                    if (kind >= 2) {
-                        const uint4 o = philox4x32_10(make_uint4(slo, shi, (uint32_t)loc, 1u), key);
-                        outcome = (int)__umulhi(o.x, kind == 2 ? 3u : 15u);
-                    }
-                    apply_fault(s, loc, outcome, sZ, sX, tz, tx);
-                    ++nf;
-                }
+                for (int step = 0; step < GEO_LOG; ++step) { const int mid = (a + c + 1) >> 1; if (r < T[mid]) a = mid; else c = mid - 1; }
+                pos += a;
+                if (a < GEO_K || pos >= hi) break;
             }
+            if (pos >= hi) break;
+            const int loc = pos++;
+            int outcome = 0;
+            const int kind = s.kind[loc];
+            if (kind >= 2) outcome = (int)__umulhi(next_word(), kind == 2 ? 3u : 15u);
+            apply_fault(s, loc, outcome, sZ, sX, tz, tx);
+            ++nf;
         }
         __syncwarp();
         tz = warp_xor(tz); tx = warp_xor(tx);
@@ -168,16 +195,34 @@ int launch_events_syndrome(qb_sampler *s, const int32_t *ev_ptr_d, const uint32_
     return QB_OK;
 }
 
+// T[k] = floor(2^32 (1-p)^k) for k = 1 .. GEO_K (T[0] unused); p in (0, 1)
+void geometric_table(double p, std::vector<uint32_t> &T)
+{
+    T.assign(GEO_K + 1, 0u);
+    const double l1p = log1p(-p);
+    for (int k = 1; k <= GEO_K; ++k) {
+        const double v = floor(4294967296.0 * exp((double)k * l1p));
+        T[k] = v >= 4294967295.0 ? 0xFFFFFFFFu : (v <= 0.0 ? 0u : (uint32_t)v);
+    }
+}
+int geometric_table_size() { return GEO_K + 1; }
+
 int launch_sample_syndrome(qb_sampler *s, uint64_t seed, uint64_t first_shot, int B, double p,
                            uint32_t *synZ, uint32_t *trueZ, uint32_t *synX, uint32_t *trueX,
                            int32_t *nfaults, cudaStream_t st)
 {
     if (B <= 0) return QB_OK;
     QB_REQUIRE(p >= 0.0 && p < 1.0, "error_rate must be in [0, 1)");
-    const uint32_t thr = (uint32_t)(p * 4294967296.0);
+    if (p > 0.0 && (s->geo_p != p || s->d_geo == nullptr)) {          // jump table of this error rate (rebuilt when p changes)
+        geometric_table(p, s->h_geo);
+        QB_CUDA(cudaStreamSynchronize(st));
+        if (!s->d_geo) { QB_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_geo), sizeof(uint32_t) * (GEO_K + 1))); s->owned.push_back(s->d_geo); }
+        QB_CUDA(cudaMemcpy(s->d_geo, s->h_geo.data(), sizeof(uint32_t) * (GEO_K + 1), cudaMemcpyHostToDevice));
+        s->geo_p = p;
+    }
     const int grid = std::max(1, std::min(ceil_div(B, SAMP_WARPS), s->sm_count * 8));
-    const size_t smem = sizeof(uint32_t) * SAMP_WARPS * (s->mwZ + s->mwX);
-    sample_syndrome_kernel<<<grid, SAMP_WARPS * 32, smem, st>>>(dev_view(s), seed, first_shot, B, thr, synZ, trueZ,
+    const size_t smem = sizeof(uint32_t) * ((GEO_K + 1) + SAMP_WARPS * (s->mwZ + s->mwX));
+    sample_syndrome_kernel<<<grid, SAMP_WARPS * 32, smem, st>>>(dev_view(s), seed, first_shot, B, p > 0.0 ? s->d_geo : nullptr, synZ, trueZ,
                                                                synX, trueX, nfaults);
     QB_CUDA(cudaGetLastError());
     return QB_OK;

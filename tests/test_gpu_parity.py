@@ -273,21 +273,42 @@ def test_philox_known_answers_and_sampler_stream():
     assert _philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     s = code_setup("72"); smp = _lib.Sampler(s["ft"]); ft = s["ft"]
     seed, first, B, p = 0x1234567812345678, (1 << 33) + 5, 6, 0.02
-    thr = int(p * 4294967296.0)
+    # host re-derivation of the documented stream (include/qldpc_b200.h, qb_sample_syndromes): lane l owns locations
+    # [l*C, (l+1)*C); geometric jumps by inversion against the library's own table; outcome word for IDLE / CNOT faults
+    T = _lib.geometric_table(p).astype(np.int64)
+    K = len(T) - 1
+    C = (smp.L + 31) // 32
+    key = [seed & 0xFFFFFFFF, seed >> 32]
     ev_ptr, ev = [0], []
     for b in range(B):
         shot = first + b
-        key = [seed & 0xFFFFFFFF, seed >> 32]
-        for q in range((smp.L + 3) // 4):
-            r = _philox4x32_10([shot & 0xFFFFFFFF, shot >> 32, q, 0], key)
-            for i in range(4):
-                loc = 4 * q + i
-                if loc < smp.L and r[i] < thr:
-                    kind = ft.loc_kind[loc]; out = 0
-                    if kind >= 2:
-                        o = _philox4x32_10([shot & 0xFFFFFFFF, shot >> 32, loc, 1], key)[0]
-                        out = (o * (3 if kind == 2 else 15)) >> 32
-                    ev.append(loc | (out << 24))
+        shot_events = []
+        for lane in range(32):
+            lo, hi = min(smp.L, lane * C), min(smp.L, lane * C + C)
+            words, call = [], 0
+
+            def next_word():
+                nonlocal call
+                if not words:
+                    words.extend(_philox4x32_10([shot & 0xFFFFFFFF, shot >> 32, lane + 32 * call, 2], key)); call += 1
+                return words.pop(0)
+
+            pos = lo
+            while True:
+                while True:
+                    r = next_word()
+                    a = int(np.sum(r < T[1:]))                       # largest k with r < T[k] (T decreasing), 0 if none
+                    pos += a
+                    if a < K or pos >= hi:
+                        break
+                if pos >= hi:
+                    break
+                loc = pos; pos += 1
+                kind = ft.loc_kind[loc]; out = 0
+                if kind >= 2:
+                    out = (next_word() * (3 if kind == 2 else 15)) >> 32
+                shot_events.append(loc | (out << 24))
+        ev += shot_events
         ev_ptr.append(len(ev))
     szb, tzb, sxb, txb, nf = smp.sample(seed, first, B, p)
     assert list(nf) == list(np.diff(ev_ptr))
@@ -305,6 +326,11 @@ def test_sampler_statistics_match_channel_probabilities():
     s = code_setup("72"); smp = _lib.Sampler(s["ft"]); p = 0.01; B = 200000
     szb, tzb, sxb, txb, nf = smp.sample(2024, 0, B, p)
     assert abs(nf.mean() - smp.L * p) < 5 * np.sqrt(smp.L * p * (1 - p) / B)
+    # independent Bernoulli locations: the number of faults per shot is Binomial(L, p) -- its variance checks the gap
+    # sampler's jumps (too regular or too bursty gaps would show here), its extremes the 32 lane chunks
+    var = smp.L * p * (1 - p)
+    assert abs(nf.var() - var) < 6 * var * np.sqrt(2.0 / B)
+    assert nf.min() >= 0 and nf.max() < smp.L * p + 8 * np.sqrt(var)
     # detector marginals: P(bit) = (1 - prod(1 - 2 p_j)) / 2 over the columns touching the detector
     M = matrices("72", p)
     for bits, H, cp in ((szb, M["HdecZ"], M["channel_probsZ"]), (sxb, M["HdecX"], M["channel_probsX"])):

@@ -305,3 +305,14 @@ def test_unmodified_reference_main_runs_up_to_the_gpu_boundary(tmp_path):
     assert "run_simulation" in res.stderr, "the failure must come from inside run_simulation"
     assert os.path.isdir(tmp_path / "matrix_cache") and len(os.listdir(tmp_path / "matrix_cache")) == 1, "the built matrices were cached"
     assert len(os.listdir(tmp_path / "codes")) == 5
+
+
+def test_sampler_jump_table():
+    """qb_sampler_geometric_table: T[k] = floor(2^32 (1-p)^k), strictly the inversion table of P(G >= k) = (1-p)^k."""
+    for p in (0.0001, 0.005, 0.02, 0.3):
+        T = _lib.geometric_table(p).astype(np.float64)
+        k = np.arange(1, 1024)
+        assert np.all(np.diff(T[1:]) <= 0)
+        np.testing.assert_allclose(T[1:] / 2.0 ** 32, (1 - p) ** k, rtol=0, atol=2.0 ** -32 * 1.5)
+    with pytest.raises(ValueError):
+        _lib.geometric_table(0.0)
