@@ -258,9 +258,15 @@ def test_ler_pinned_to_real_reference(tag, p, max_iter, shots, philox_shots):
     """tests/golden/ler.npz holds (z_err, x_err) per shot from the REAL reference's _run_single_trial_fast
     (engine.py:68-122; dynamical alpha, OSD-0, seeds 1234 + i; generator: tests/golden/make_ler_golden.py).
       (a) identical faults: the reference's np.random stream is replayed on the host and fed to the pipeline as
-          explicit fault events -- per-shot flags are compared one by one (sides the reference's min-sum converged on
-          are exact; OSD sides can differ where its unstable float64 argsort breaks ties differently);
-      (b) the Philox-sampled LER of the GPU pipeline lies inside the reference's 95 % Clopper-Pearson interval."""
+          explicit fault events -- per-shot flags are compared one by one.  Measured (tests/ler_probe.py): gross code
+          4000 shots z 100 % / x 99.98 % equal (1996 against 1995 logical errors), 72 code 4000 of 4000, 90 / 108 codes
+          >= 99.9 %; the rare differences are OSD sides where float32 against float64 posteriors (and the reference's
+          unstable argsort) order near-ties differently.  [[288,12,18]] at maxIter = 100: 82 % (see below).
+      (b) the Philox-sampled LER of the GPU pipeline lies inside the reference's Clopper-Pearson interval.  The interval
+          asserted is the 99.7 % one: with nine configurations a 95 % interval fails by chance every other run -- e.g. the
+          reference's own 3000-shot sample for the 108 code at p = 0.004 (558 errors) sits 2.4 sigma above the LER that
+          524 288 GPU shots AND the reference's flags on identical faults (558 of 558) agree on; the 95 % interval is
+          printed in the failure message."""
     from qldpc_b200.simulation.engine import ShotEngine
     g = np.load(os.path.join(GOLDEN, "ler.npz"))
     key = f"{tag}_{int(round(p * 1e4))}"
@@ -271,7 +277,7 @@ def test_ler_pinned_to_real_reference(tag, p, max_iter, shots, philox_shots):
     rz = np.unpackbits(g[key + "_z"], bitorder="little")[:shots].astype(bool)
     rx = np.unpackbits(g[key + "_x"], bitorder="little")[:shots].astype(bool)
     s = code_setup(tag); M = matrices(tag, p)
-    nrep = min(shots, 2000 if tag != "288" else 240)
+    nrep = min(shots, 3000 if tag != "288" else 240)
     eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=max(nrep, min(philox_shots, 32768)))
     cfg = _lib.make_config(max_iter, _lib.QB_ALPHA_DYNAMIC)
     ev_ptr, ev = _reference_stream_events(s["cc"], nrep, p)
@@ -280,19 +286,19 @@ def test_ler_pinned_to_real_reference(tag, p, max_iter, shots, philox_shots):
     agree_z, agree_x = (ez == rz[:nrep]).mean(), (ex == rx[:nrep]).mean()
     # [[288,12,18]] at maxIter = 100: 99.5 % of the sides reach OSD with posteriors of 100 non-linear iterations, float32
     # and float64 orderings differ substantially there and so do the (equally valid) OSD-0 corrections; measured 0.82.
-    bar = 0.97 if tag != "288" else 0.75
+    bar = 0.995 if tag != "288" else 0.75
     assert agree_z >= bar and agree_x >= bar, (agree_z, agree_x)
     # the same shots give statistically the same LER (paired: differences only from tie-breaking in the OSD order)
     ref_tot = (rz | rx)[:nrep].sum(); mine_tot = (ez | ex).sum()
-    assert abs(int(ref_tot) - int(mine_tot)) <= max(5, (0.03 if tag != "288" else 0.08) * nrep), (ref_tot, mine_tot)
+    assert abs(int(ref_tot) - int(mine_tot)) <= max(3, (0.003 if tag != "288" else 0.08) * nrep), (ref_tot, mine_tot)
     # (b) Philox LER inside the reference's interval (widened by the GPU estimate's own 2-sigma)
     c2, _ = eng.pipeline.run(1234, 0, philox_shots, p, cfg)
     eng.close()
     k_ref = int((rz | rx).sum())
-    lo, hi = _clopper_pearson(k_ref, shots)
+    lo, hi = _clopper_pearson(k_ref, shots, conf=0.997)
     ler = c2[2] / c2[3]
     slack = 2.0 * np.sqrt(max(ler * (1 - ler), 1e-9) / c2[3])
-    assert lo - slack <= ler <= hi + slack, (key, ler, (lo, hi), k_ref, shots)
+    assert lo - slack <= ler <= hi + slack, (key, ler, "99.7 %", (lo, hi), "95 %", _clopper_pearson(k_ref, shots), k_ref, shots)
     for cnt, ref in ((c2[0], rz), (c2[1], rx)):
-        lo_s, hi_s = _clopper_pearson(int(ref.sum()), shots, conf=0.99)
+        lo_s, hi_s = _clopper_pearson(int(ref.sum()), shots, conf=0.997)
         assert lo_s - slack <= cnt / c2[3] <= hi_s + slack, (key, cnt / c2[3], (lo_s, hi_s))
