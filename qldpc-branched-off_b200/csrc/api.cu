@@ -807,6 +807,7 @@ static int decode_batch(qb_pipeline *p, qb_workspace &W, qb_workspace &other, in
         a.final_iter = side ? W.itX : W.itZ; a.post = side ? W.postX : W.postZ; a.post_failed_only = 1;
         a.fail_count = W.nfail + side; a.fail_idx = side ? W.failX : W.failZ; a.fail_wt = side ? W.fwX : W.fwZ;
         a.precision = cfg->precision;
+        if (!cfg->use_osd && getenv("QLDPC_B200_NO_POST")) a.post = nullptr;     // measurement aid: min-sum without the posterior output
         if (int rc = launch_minsum(d, a, st)) return rc;
         p->stats.kernel_launches++;
     }

@@ -8,7 +8,7 @@ B = int(sys.argv[1]); tag = sys.argv[2] if len(sys.argv) > 2 else "144"; p = flo
 s = helpers.code_setup(tag); M = helpers.matrices(tag, p)
 eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=B)
 import os
-cfg = _lib.make_config(int(os.environ.get("QB_MAX_ITER", "20")), _lib.QB_ALPHA_DYNAMIC, precision=int(os.environ.get("QB_PRECISION", "0")))
+cfg = _lib.make_config(int(os.environ.get("QB_MAX_ITER", "20")), _lib.QB_ALPHA_DYNAMIC, precision=int(os.environ.get("QB_PRECISION", "0")), use_osd=os.environ.get("QB_NO_OSD") is None)
 for it in range(int(sys.argv[4]) if len(sys.argv) > 4 else 3):
     t0 = time.time()
     counts, _ = eng.pipeline.run(1234, it * B, B, p, cfg)
