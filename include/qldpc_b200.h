@@ -229,7 +229,8 @@ int qb_pipeline_run(qb_pipeline *p, uint64_t seed, uint64_t first_shot, int64_t 
 
 /* Same pipeline fed with host fault events instead of the Philox sampler (parity testing against the
  * reference on identical host-sampled error batches; also the `e2e` bench path: host buffers in,
- * flags out).  Optional per-shot outputs (nullable): converged_h [2][B], final_iter_h [2][B]. */
+ * flags out).  B may exceed the pipeline's max_batch: the events go up in one copy and the batches are pipelined over
+ * the two workspaces.  Optional per-shot outputs (nullable, B <= max_batch only): converged_h [2][B], final_iter_h [2][B]. */
 int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const uint32_t *events_h, int32_t B,
                                 const qb_decode_config *cfg, int64_t *counts_h, uint8_t *flags_h,
                                 uint8_t *converged_h, int32_t *final_iter_h);

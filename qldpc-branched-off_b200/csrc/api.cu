@@ -729,6 +729,7 @@ struct qb_pipeline {
     cudaEvent_t ev_begin = nullptr, ev_tail = nullptr;   // run start (second stream waits for it) / second stream drained
     int64_t *counts = nullptr;   // device [8]
     int32_t *ev_ptr = nullptr; uint32_t *events = nullptr; size_t ev_cap = 0;
+    int32_t *ev_ptr_big = nullptr; size_t ev_ptr_cap = 0;      // event offsets of a whole qb_pipeline_run_events_host call
     int8_t *syn8 = nullptr;      // staging for decode_host
     int detail = 0;              // qb_pipeline_enable_detail
     int last_B = 0, last_ws = 0; // shots / workspace of the last batch (what qb_pipeline_last_batch_detail may read)
@@ -945,6 +946,7 @@ void qb_pipeline_destroy(qb_pipeline *p)
     cudaDeviceSynchronize();
     for (void *q : p->owned) cudaFree(q);
     if (p->events) cudaFree(p->events);
+    if (p->ev_ptr_big) cudaFree(p->ev_ptr_big);
     for (auto e : p->evs) if (e) cudaEventDestroy(e);
     for (int w = 0; w < 2; ++w) {
         qb_workspace &W = p->ws[w];
@@ -995,7 +997,8 @@ int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const u
 {
     QB_REQUIRE(p && ev_ptr_h && counts_h, "NULL argument");
     QB_REQUIRE(p->s != nullptr, "pipeline was created without a sampler");
-    QB_REQUIRE(B >= 0 && B <= p->max_batch, "batch exceeds the pipeline's max_batch");
+    QB_REQUIRE(B >= 0, "negative number of shots");
+    QB_REQUIRE(B <= p->max_batch || (!converged_h && !final_iter_h), "per-shot detail is available for a single batch (B <= max_batch) only");
     if (int rc = check_cfg(cfg)) return rc;
     QB_CUDA(cudaSetDevice(p->dz->device));
     p->stats = qb_pipeline_stats{};
@@ -1008,25 +1011,42 @@ int qb_pipeline_run_events_host(qb_pipeline *p, const int32_t *ev_ptr_h, const u
         QB_CUDA(cudaMalloc(&p->events, (nev + nev / 2 + 1024) * 4));
         p->ev_cap = nev + nev / 2 + 1024;
     }
+    if ((size_t)B + 1 > p->ev_ptr_cap) {
+        if (p->ev_ptr_big) cudaFree(p->ev_ptr_big);
+        p->ev_ptr_big = nullptr; p->ev_ptr_cap = 0;
+        QB_CUDA(cudaMalloc(&p->ev_ptr_big, ((size_t)B + 1 + (size_t)B / 2) * 4));
+        p->ev_ptr_cap = (size_t)B + 1 + (size_t)B / 2;
+    }
     if (int rc = begin_run(p, cfg)) return rc;
-    qb_workspace &W = p->ws[0];
     QB_CUDA(cudaEventRecord(p->evs[EV_START], p->st));
-    QB_CUDA(cudaMemcpyAsync(p->ev_ptr, ev_ptr_h, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, p->st));
+    // all fault events of the call go up in one copy; the batches (max_batch shots each) then alternate between the two
+    // workspaces like in qb_pipeline_run, the event offsets stay absolute
+    QB_CUDA(cudaMemcpyAsync(p->ev_ptr_big, ev_ptr_h, ((size_t)B + 1) * 4, cudaMemcpyHostToDevice, p->st));
     if (nev) QB_CUDA(cudaMemcpyAsync(p->events, events_h, nev * 4, cudaMemcpyHostToDevice, p->st));
-    if (int rc = launch_events_syndrome(p->s, p->ev_ptr, p->events, B, W.synZ, W.trueZ, W.synX, W.trueX, p->st)) return rc;
-    p->stats.kernel_launches++;
-    QB_CUDA(cudaEventRecord(p->evs[EV_SAMPLED], p->st));
-    if (int rc = decode_batch(p, W, p->ws[1], B, cfg, 0)) return rc;
-    if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h, W.flags, (size_t)B, cudaMemcpyDeviceToHost, p->st));
+    QB_CUDA(cudaEventRecord(p->ev_begin, p->st));
+    QB_CUDA(cudaStreamWaitEvent(p->ws[1].st, p->ev_begin, 0));
+    int nb = 0;
+    for (int done = 0; done < B; done += p->max_batch, ++nb) {
+        const int Bi = std::min(p->max_batch, B - done);
+        qb_workspace &W = p->ws[nb & 1], &O = p->ws[(nb & 1) ^ 1];
+        if (nb > 0 && nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_START], W.st));
+        if (int rc = launch_events_syndrome(p->s, p->ev_ptr_big + done, p->events, Bi, W.synZ, W.trueZ, W.synX, W.trueX, W.st)) return rc;
+        p->stats.kernel_launches++;
+        if (nb < MAX_TIMED_BATCHES) QB_CUDA(cudaEventRecord(p->evs[(size_t)nb * EV_PER_BATCH + EV_SAMPLED], W.st));
+        if (int rc = decode_batch(p, W, O, Bi, cfg, nb)) return rc;
+        if (flags_h) QB_CUDA(cudaMemcpyAsync(flags_h + done, W.flags, (size_t)Bi, cudaMemcpyDeviceToHost, W.st));
+    }
     if (converged_h) {
+        qb_workspace &W = p->ws[0];
         QB_CUDA(cudaMemcpyAsync(converged_h, W.convZ, (size_t)B, cudaMemcpyDeviceToHost, p->st));
         QB_CUDA(cudaMemcpyAsync(converged_h + B, W.convX, (size_t)B, cudaMemcpyDeviceToHost, p->st));
     }
     if (final_iter_h) {
+        qb_workspace &W = p->ws[0];
         QB_CUDA(cudaMemcpyAsync(final_iter_h, W.itZ, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
         QB_CUDA(cudaMemcpyAsync(final_iter_h + B, W.itX, (size_t)B * 4, cudaMemcpyDeviceToHost, p->st));
     }
-    return finish_run(p, 1, counts_h);
+    return finish_run(p, nb, counts_h);
 }
 
 int qb_pipeline_decode_host(qb_pipeline *p, const int8_t *sparseZ_h, const uint32_t *trueZ_h, const int8_t *sparseX_h,

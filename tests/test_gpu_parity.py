@@ -729,3 +729,23 @@ def test_run_simulation_two_ranks_nccl(tmp_path):
     a = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, num_trials=6000, base_seed=11, batch_size=4096, **kw)
     b = run_simulation(s["Hx"], s["Hz"], s["Lx"], s["Lz"], p, base_seed=11, target_logical_errors=40, max_trials=6000, batch_size=700, **kw)
     assert [a["logical_errors"], a["num_trials"], b["logical_errors"], b["num_trials"]] == two.tolist()
+
+
+def test_run_events_host_pipelines_several_batches():
+    """qb_pipeline_run_events_host with more shots than max_batch: one upload, batches alternating between the two
+    workspaces -- flags and counters equal those of batch-sized calls."""
+    from qldpc_b200.simulation.engine import ShotEngine
+    s = code_setup("72"); p = 0.006; M = matrices("72", p)
+    eng = ShotEngine(s["cc"], s["Lx"], s["Lz"], M, max_batch=500)
+    cfg = _lib.make_config(20, _lib.QB_ALPHA_DYNAMIC)
+    ev_ptr, ev = _host_events(s["ft"], 1730, p, seed=5)              # 3 full batches + a ragged one
+    c_all, f_all = eng.pipeline.run_events(ev_ptr, ev, cfg)
+    tot = np.zeros(8, dtype=np.int64); parts = []
+    for lo in range(0, 1730, 500):
+        hi = min(1730, lo + 500)
+        c, f = eng.pipeline.run_events(ev_ptr[lo:hi + 1] - ev_ptr[lo], ev[ev_ptr[lo]:ev_ptr[hi]], cfg)
+        tot += c; parts.append(f)
+    assert np.array_equal(np.concatenate(parts), f_all) and np.array_equal(tot, c_all) and c_all[3] == 1730
+    with pytest.raises(ValueError):
+        eng.pipeline.run_events(ev_ptr, ev, cfg, want_detail=True)    # per-shot detail: single batch only
+    eng.close()
