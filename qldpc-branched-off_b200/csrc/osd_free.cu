@@ -551,7 +551,8 @@ int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d,
     P.g = g; P.a = a; P.F = a.F;
     P.cap = pl.cap; P.cap_per_wt = pl.cap_per_wt; P.max_wt = pl.max_wt;
     const int gridA = std::max(1, std::min(ceil_div(a.F, pl.A.warps), dec->sm_count * pl.A.ctas_per_sm));
-    const int gridB = std::max(1, std::min(ceil_div(a.F, pl.B.warps), dec->sm_count * pl.B.ctas_per_sm));
+    int gridB = std::max(1, std::min(ceil_div(a.F, pl.B.warps), dec->sm_count * pl.B.ctas_per_sm));
+    if (const char *e = getenv("QLDPC_B200_OSD_GRID_B")) { const int v = atoi(e); if (v >= 1) gridB = std::min(gridB, v); }
     const int sel_ctas = (int)std::max<size_t>(1, std::min<size_t>(2048 / SELF_THREADS, ((size_t)dec->max_smem_optin + 1024) / (pl.smem_sel + 1024)));
     const int grid_sel = std::max(1, std::min(a.F, dec->sm_count * sel_ctas));
     const size_t slotsA = (size_t)gridA * pl.A.warps, slotsB = (size_t)gridB * pl.B.warps;

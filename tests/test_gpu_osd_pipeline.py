@@ -302,3 +302,38 @@ def test_ler_pinned_to_real_reference(tag, p, max_iter, shots, philox_shots):
     for cnt, ref in ((c2[0], rz), (c2[1], rx)):
         lo_s, hi_s = _clopper_pearson(int(ref.sum()), shots, conf=0.997)
         assert lo_s - slack <= cnt / c2[3] <= hi_s + slack, (key, cnt / c2[3], (lo_s, hi_s))
+
+
+def test_pipeline_osd_small_and_awkward_graphs():
+    """The free-row path on graphs far from the BB codes: fewer than 32 rows / 256 columns (window larger than the
+    problem), column degree up to 8, empty rows and columns, duplicate reliabilities, all-zero residuals, a batch of one;
+    and a graph with a column of degree > 8 (no column signatures: the full-width kernel takes the whole queue)."""
+    rng = np.random.default_rng(77)
+    for (m, n, w) in ((3, 7, 3), (20, 60, 4), (90, 500, 8), (200, 3000, 6), (40, 30, 3), (64, 300, 12)):
+        H = np.zeros((m, n), dtype=np.int64)
+        for j in range(n):
+            H[rng.choice(m, size=rng.integers(1, min(w, m) + 1), replace=False), j] = 1
+        if n > 10:
+            H[:, 5] = 0
+        if m > 10:
+            H[m // 2, :] = 0
+        Hc = csr_matrix(H); col_ptr, row_idx = orc._csc(H)
+        dec = _lib.Decoder(Hc.indptr, Hc.indices, n, np.ones(n))
+        for B in (1, 37):
+            e = (rng.random((B, n)) < 0.08).astype(np.int8)
+            syn = ((e.astype(np.int64) @ H.T) % 2).astype(np.int8)
+            hard = (rng.random((B, n)) < 0.03).astype(np.int8)
+            if B > 3:
+                hard[3] = e[3]                                     # zero residual: nothing to do
+            post = np.round(rng.normal(size=(B, n)) * 2, 1).astype(np.float32)     # many exact ties
+            post[e != 0] *= np.float32(0.1)
+            sol, info = dec.osd0_pipeline(syn, hard, post)
+            for b in range(B):
+                order = np.argsort(np.abs(post[b]), kind="stable")
+                ref, _ = orc.osd0_csc(col_ptr, row_idx, m, n, syn[b], hard[b], order)
+                assert np.array_equal(sol[b].astype(np.int64), ref), (m, n, w, B, b, info[b] >> 16)
+            if w > 8:
+                assert ((info >> 16) == 2).all(), "columns of degree > 8: full-width kernel"
+            else:
+                assert ((info >> 16) == 1).sum() >= 0.8 * B, (m, n, (info >> 16).tolist())
+        dec.close()
