@@ -558,9 +558,9 @@ int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d,
     const size_t slotsA = (size_t)gridA * pl.A.warps, slotsB = (size_t)gridB * pl.B.warps;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t F = (size_t)a.F;
-    // sides the second selection pass has buffers for: 1/16 of the queue where ~1 % leave tier A (m <= 1536), 1/4 for the
-    // large codes (the [[288,12,18]] code at p = 0.006: 12 %)
-    const size_t F2 = std::max<size_t>(64, g.m <= 1536 ? F / 16 : F / 4);
+    // sides the second selection pass has buffers for: 1/8 of the queue where 1-4 % leave tier A (m <= 1536; gross code
+    // 1.1 % at p = 0.005, 3.6 % at p = 0.006), 1/4 for the large codes (the [[288,12,18]] code at p = 0.006: 12 %)
+    const size_t F2 = std::max<size_t>(64, g.m <= 1536 ? F / 8 : F / 4);
     const size_t need = 256 + al(F * pl.cap * 2) + al(F * 4) + al(F * g.mw * 4) + al(slotsA * pl.A.rec_cap * 4) + al(slotsA * pl.A.rcap * 4) +
                         al(slotsB * pl.B.rec_cap * 4) + al(slotsB * pl.B.rcap * 4) + 4 * al(F * 4) + al(F2 * pl.cap2 * 2) + al(F2 * 4);
     const bool grown = dec->ovf.cap < need;
