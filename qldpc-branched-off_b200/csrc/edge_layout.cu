@@ -39,7 +39,7 @@ std::vector<std::vector<int>> lpt(const std::vector<int> &cost, int nwarps)
 }  // namespace
 
 EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t *indices, const float *prior,
-                             int nwarps, uint64_t seed)
+                             int nwarps, uint64_t seed, const uint8_t *phantom)
 {
     EdgeLayout L;
     L.m = m; L.n = n; L.nnz = m > 0 ? indptr[m] : 0; L.nwarps = nwarps;
@@ -104,8 +104,8 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     struct CSlice { std::vector<int> vars; int deg; int exact; float prior; int cls; };
     std::vector<CSlice> csl;
     {
-        std::vector<int> order(n);
-        std::iota(order.begin(), order.end(), 0);
+        std::vector<int> order;
+        for (int j = 0; j < n; ++j) if (!phantom || !phantom[j]) order.push_back(j);      // phantom columns only reserve slots
         auto key = [&](int j) {
             uint32_t b = 0;
             if (L.uniform_prior) memcpy(&b, &prior[j], 4);
@@ -193,7 +193,9 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     {   // greedy, group by group
         std::vector<int> by_group(nnz);
         std::iota(by_group.begin(), by_group.end(), 0);
-        std::stable_sort(by_group.begin(), by_group.end(), [&](int a, int b) { return edge_group[a] < edge_group[b]; });
+        // (edges of phantom columns belong to no gather group: they take whatever slot is left, after the others)
+        std::stable_sort(by_group.begin(), by_group.end(), [&](int a, int b) {
+            return (edge_group[a] < 0 ? (1 << 30) : edge_group[a]) < (edge_group[b] < 0 ? (1 << 30) : edge_group[b]); });
         for (int e : by_group) {
             const int r = edge_row[e], g = edge_group[e];
             const int nslots = rsl[row_slice[r]].K * 4;
@@ -202,24 +204,24 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
             for (int q = 0; q < nslots; ++q) {
                 const int s = (start + q) % nslots;
                 if (owner[(size_t)r * maxK * 4 + s] >= 0) continue;
-                const int c = gcnt[(size_t)g * 32 + bank_of(r, s)];
+                const int c = g < 0 ? 0 : gcnt[(size_t)g * 32 + bank_of(r, s)];
                 if (c < best_cost) { best_cost = c; best = s; if (c == 0) break; }
             }
             if (best < 0) return fail("internal: no free slot");
             slot_of[e] = best; owner[(size_t)r * maxK * 4 + best] = e;
-            gcnt[(size_t)g * 32 + bank_of(r, best)]++;
+            if (g >= 0) gcnt[(size_t)g * 32 + bank_of(r, best)]++;
         }
     }
     auto n_conflicted = [&]() {
         int c = 0;
-        for (int e = 0; e < nnz; ++e) if (gcnt[(size_t)edge_group[e] * 32 + bank_of(edge_row[e], slot_of[e])] > 1) ++c;
+        for (int e = 0; e < nnz; ++e) if (edge_group[e] >= 0 && gcnt[(size_t)edge_group[e] * 32 + bank_of(edge_row[e], slot_of[e])] > 1) ++c;
         return c;
     };
     {   // min-conflicts local search: move a conflicted edge to another slot of its row (swapping with the occupant)
         std::vector<int> bad;
         for (int pass = 0; pass < 200; ++pass) {
             bad.clear();
-            for (int e = 0; e < nnz; ++e) if (gcnt[(size_t)edge_group[e] * 32 + bank_of(edge_row[e], slot_of[e])] > 1) bad.push_back(e);
+            for (int e = 0; e < nnz; ++e) if (edge_group[e] >= 0 && gcnt[(size_t)edge_group[e] * 32 + bank_of(edge_row[e], slot_of[e])] > 1) bad.push_back(e);
             if (bad.empty()) break;
             for (size_t i = bad.size(); i > 1; --i) std::swap(bad[i - 1], bad[rng.below((uint32_t)i)]);
             for (int e : bad) {
@@ -233,7 +235,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                     if (b2 == b) continue;
                     const int e2 = owner[(size_t)r * maxK * 4 + s2];
                     int delta = (gcnt[(size_t)g * 32 + b2] >= 1 ? 1 : 0) - 1;
-                    if (e2 >= 0) {
+                    if (e2 >= 0 && edge_group[e2] >= 0) {
                         const int g2 = edge_group[e2];
                         if (g2 == g) continue;                               // same multiset of banks
                         delta += (gcnt[(size_t)g2 * 32 + b] >= 1 ? 1 : 0) - (gcnt[(size_t)g2 * 32 + b2] >= 2 ? 1 : 0);
@@ -248,7 +250,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                 slot_of[e] = s2; owner[(size_t)r * maxK * 4 + s2] = e; owner[(size_t)r * maxK * 4 + s] = e2;
                 if (e2 >= 0) {
                     const int g2 = edge_group[e2];
-                    gcnt[(size_t)g2 * 32 + b2]--; gcnt[(size_t)g2 * 32 + b]++;
+                    if (g2 >= 0) { gcnt[(size_t)g2 * 32 + b2]--; gcnt[(size_t)g2 * 32 + b]++; }
                     slot_of[e2] = s;
                 }
             }
@@ -287,6 +289,10 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
             }
         }
     }
+    L.edge_slot.assign(nnz, 0u);
+    L.row_pos.assign(m, 0u);
+    for (int r = 0; r < m; ++r) L.row_pos[r] = (uint32_t)(row_slice[r] * 32 + row_lane[r]);
+    for (int e = 0; e < nnz; ++e) L.edge_slot[e] = (uint32_t)slot_word(row_slice[edge_row[e]], row_lane[edge_row[e]], slot_of[e]);
     L.row_mask.assign((size_t)L.n_rsl * 32, 0u);
     {
         Rng mr(seed ^ 0xD1B54A32D192ED03ull);

@@ -61,6 +61,8 @@ struct EdgeLayout {
     std::vector<uint32_t> col_rowpos;    // [idx_words] permuted row position (slice*32+lane) pairs, same layout
     std::vector<float> lane_prior;       // [n_csl*32] (only when !uniform_prior)
     std::vector<int32_t> slot_var;       // [e_words] variable of each slot, -1 = unused (+inf), -2 = dummy (0)
+    std::vector<uint32_t> edge_slot;     // [nnz] word of E that holds the edge (CSR edge order)
+    std::vector<uint32_t> row_pos;       // [m] permuted position (slice * 32 + lane) of every row
     std::vector<int32_t> wr_ptr, wc_ptr; // [nwarps+1]
     // column slices of a warp are sorted by class: 0..8 = full slice of degree 0..8, uniform prior;
     // 9..14 = same for variables next to a degree-1 row (NaN handling), degree 1..6; 15 = everything else
@@ -76,7 +78,9 @@ struct EdgeLayout {
 };
 
 // prior: float priors (finite).  slack: extra free slots per row beyond the mandatory one.
+// phantom (nullable, [n]): columns that only reserve a slot per edge in their rows -- their variable is processed by
+// another CTA of a cluster or by the cluster kernel's own list (minsum_edge_cluster.cu) -- and get no column slice.
 EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t *indices, const float *prior,
-                             int nwarps, uint64_t seed = 0x9E3779B97F4A7C15ull);
+                             int nwarps, uint64_t seed = 0x9E3779B97F4A7C15ull, const uint8_t *phantom = nullptr);
 
 }  // namespace qb
