@@ -76,6 +76,11 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior_h);
  * it from qb_decode_config).  QB_PRECISION_HALF2 fails with QB_ERR_UNSUPPORTED at decode time when the graph has no
  * per-edge plan; it never silently falls back. */
 int qb_decoder_set_precision(qb_decoder *dec, int32_t precision);
+/* Which float32 min-sum kernel the handle uses for damping == 1 (a property of the graph and the priors): 0 = the
+ * compressed-state kernel (csrc/minsum.cu), 1 = one float per edge in the shared memory of one SM
+ * (csrc/minsum_edge.cu), N >= 2 = the same on a thread-block cluster of N SMs, check rows cut into N slabs
+ * (csrc/minsum_edge_cluster.cu; the [[288,12,18]] decoding graphs).  All three follow src/decoding/kernels.py:235-366. */
+int qb_decoder_minsum_path(qb_decoder *dec);
 
 /* Host-only (no CUDA call): statistics of the shared-memory layout the per-edge min-sum kernel would use for this
  * graph (csrc/edge_layout.h): one float per Tanner-graph edge, check rows in conflict-free 128-bit order, the slot of

@@ -46,7 +46,7 @@ EXPORTS = [
     "qb_sampler_destroy", "qb_syndrome_from_events", "qb_syndrome_from_events_host", "qb_sample_syndromes",
     "qb_pipeline_create", "qb_pipeline_destroy", "qb_pipeline_set_stream", "qb_pipeline_run", "qb_pipeline_run_events_host",
     "qb_pipeline_decode_host", "qb_pipeline_last_stats", "qb_pipeline_enable_detail", "qb_pipeline_last_batch_detail",
-    "qb_osd0_pipeline_host", "qb_decoder_osd_stats", "qb_decoder_set_precision",
+    "qb_osd0_pipeline_host", "qb_decoder_osd_stats", "qb_decoder_set_precision", "qb_decoder_minsum_path",
     "qb_sampler_geometric_table",
 ]
 
@@ -137,6 +137,10 @@ class Decoder:
     def set_precision(self, precision):
         """QB_PRECISION_F32 (default) or QB_PRECISION_HALF2 (packed opt-in mode) for this handle's min-sum calls."""
         check(load().qb_decoder_set_precision(self._h, int(precision)))
+
+    def minsum_path(self):
+        """0 = compressed-state kernel, 1 = per-edge kernel on one SM, N >= 2 = per-edge kernel on a cluster of N SMs."""
+        return int(load().qb_decoder_minsum_path(self._h))
 
     def set_prior(self, prior):
         prior = np.ascontiguousarray(prior, dtype=np.float64)

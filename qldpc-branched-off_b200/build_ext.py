@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "minsum.cu", "minsum_edge.cu", "minsum_edge_h2.cu", "edge_layout.cu", "osd.cu", "osd_free.cu", "sampler.cu"]
+SOURCES = ["api.cu", "minsum.cu", "minsum_edge.cu", "minsum_edge_h2.cu", "minsum_edge_cluster.cu", "edge_layout.cu", "osd.cu", "osd_free.cu", "sampler.cu"]
 OUT = os.environ.get("QB_BUILD_OUT", os.path.join(HERE, "libqldpc_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 OBJDIR = os.path.join(HERE, "..", "build", "obj")

@@ -231,6 +231,7 @@ int qb_decoder_create(int device, int32_t m, int32_t n, const int32_t *indptr, c
     if (!rc && !colsig.empty()) { rc = to_device(d->owned, colsig, &p16); g.colsig = reinterpret_cast<const uint4 *>(p16); }
 #undef UP
     if (!rc && !g.nan_anywhere) rc = edge_plan_create(d, pf.data(), &d->edge);
+    if (!rc && !g.nan_anywhere && !d->edge) rc = cluster_plan_create(d, pf.data(), &d->cluster);
     if (rc) { qb_decoder_destroy(d); return rc; }
     *out = d;
     return QB_OK;
@@ -251,9 +252,14 @@ int qb_decoder_set_prior(qb_decoder *dec, const double *prior)
     dec->edge_h2 = nullptr;
     edge_plan_destroy(dec->edge);
     dec->edge = nullptr;
+    cluster_plan_destroy(dec->cluster);
+    dec->cluster = nullptr;
     // same predicate as qb_decoder_create: non-finite priors or a graph that can produce NaN posteriors on its own
     // (a variable on two degree-1 rows) stay on the exact compressed-state kernel
-    if (!dec->g.nan_anywhere) return edge_plan_create(dec, pf.data(), &dec->edge);
+    if (!dec->g.nan_anywhere) {
+        if (int rc = edge_plan_create(dec, pf.data(), &dec->edge)) return rc;
+        if (!dec->edge) return cluster_plan_create(dec, pf.data(), &dec->cluster);
+    }
     return QB_OK;
 }
 
@@ -265,6 +271,13 @@ int qb_decoder_set_precision(qb_decoder *dec, int32_t precision)
     return QB_OK;
 }
 
+int qb_decoder_minsum_path(qb_decoder *dec)
+{
+    if (!dec) return 0;
+    if (dec->edge) return 1;
+    return cluster_plan_size(dec->cluster);
+}
+
 void qb_decoder_destroy(qb_decoder *dec)
 {
     if (!dec) return;
@@ -272,6 +285,7 @@ void qb_decoder_destroy(qb_decoder *dec)
     for (void *p : dec->owned) cudaFree(p);
     edge_plan_h2_destroy(dec->edge_h2);
     edge_plan_destroy(dec->edge);
+    cluster_plan_destroy(dec->cluster);
     if (dec->d_alpha) cudaFree(dec->d_alpha);
     dec->scratch.release(); dec->work.release(); dec->ovf.release();
     delete dec;

@@ -69,6 +69,7 @@ struct GraphDev {
 
 struct EdgePlan;   // per-edge min-sum kernel: layout + device tables (minsum_edge.cu)
 struct EdgePlanH2; // its packed half2 companion (minsum_edge_h2.cu)
+struct ClusterPlan; // per-edge kernel on a thread-block cluster for graphs larger than one SM (minsum_edge_cluster.cu)
 }  // namespace qb
 
 struct qb_decoder {
@@ -89,6 +90,7 @@ struct qb_decoder {
     int max_smem_optin = 0;
     qb::EdgePlan *edge = nullptr;   // nullptr: graph does not fit the per-edge kernel
     qb::EdgePlanH2 *edge_h2 = nullptr;   // packed mode, built on first use
+    qb::ClusterPlan *cluster = nullptr;  // only when edge == nullptr: the graph cut into slabs over a cluster of CTAs
     std::vector<float> h_prior;     // float priors as the kernels see them
     int precision = 0;              // QB_PRECISION_* used by the host-buffer entry points (qb_decoder_set_precision)
 };
@@ -133,6 +135,10 @@ int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st);
 int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out);
 void edge_plan_destroy(EdgePlan *p);
 int launch_minsum_edge(qb_decoder *dec, EdgePlan *p, const MinsumLaunch &a, cudaStream_t st);
+int cluster_plan_create(const qb_decoder *dec, const float *prior_h, ClusterPlan **out);
+void cluster_plan_destroy(ClusterPlan *p);
+int cluster_plan_size(const ClusterPlan *p);
+int launch_minsum_cluster(qb_decoder *dec, ClusterPlan *p, const MinsumLaunch &a, cudaStream_t st);
 int upload_alpha(qb_decoder *dec, int max_iter, int alpha_mode, double alpha, const double *seq, int len,
                  cudaStream_t st);
 

@@ -39,8 +39,9 @@ std::vector<std::vector<int>> lpt(const std::vector<int> &cost, int nwarps)
 }  // namespace
 
 EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t *indices, const float *prior,
-                             int nwarps, uint64_t seed, const uint8_t *phantom)
+                             int nwarps, uint64_t seed, const uint8_t *phantom, int rows_per_slice)
 {
+    const int rcap = std::max(8, std::min(32, rows_per_slice));
     EdgeLayout L;
     L.m = m; L.n = n; L.nnz = m > 0 ? indptr[m] : 0; L.nwarps = nwarps;
     auto fail = [&](const char *why) { L.ok = false; L.why = why; return L; };
@@ -77,7 +78,7 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
             const int deg = indptr[r + 1] - indptr[r];
             const int K = deg == 0 ? 0 : (deg + 1 + 3) / 4;
             bool joined = false;
-            if (!rsl.empty() && (int)rsl.back().rows.size() < 32) {
+            if (!rsl.empty() && (int)rsl.back().rows.size() < rcap) {
                 const int Ks = rsl.back().K;
                 if ((Ks == 0 && deg == 0) || (Ks > 0 && deg > 0 && 4 * Ks - deg <= 4)) joined = true;
             }

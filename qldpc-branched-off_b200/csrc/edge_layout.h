@@ -80,7 +80,9 @@ struct EdgeLayout {
 // prior: float priors (finite).  slack: extra free slots per row beyond the mandatory one.
 // phantom (nullable, [n]): columns that only reserve a slot per edge in their rows -- their variable is processed by
 // another CTA of a cluster or by the cluster kernel's own list (minsum_edge_cluster.cu) -- and get no column slice.
+// rows_per_slice (8..32): fewer rows per slice spread a small number of rows over all warps.
 EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t *indices, const float *prior,
-                             int nwarps, uint64_t seed = 0x9E3779B97F4A7C15ull, const uint8_t *phantom = nullptr);
+                             int nwarps, uint64_t seed = 0x9E3779B97F4A7C15ull, const uint8_t *phantom = nullptr,
+                             int rows_per_slice = 32);
 
 }  // namespace qb

@@ -143,6 +143,8 @@ struct ColCtx {
     const uint16_t *vid;    // next task's variable id of the lane (posterior output)
     uint32_t vid_next;      // its value, loaded one task ahead
     float *post;            // posterior row of the shot
+    uint32_t win;           // bits 24+ of the CTA's shared window (rank of the CTA in its cluster; 0 without clusters): the
+                            // 16-bit slot indices are word offsets inside the window
 };
 
 // index words of task (t + j) of a run of degree-D slices starting at c.ix: two words per LDS.64
@@ -174,13 +176,13 @@ __device__ __forceinline__ void group_load_idx(const ColCtx &c, int g, uint32_t 
 }
 
 template <int D, int N>
-__device__ __forceinline__ void group_gather(const uint32_t (&w)[N][(D + 1) / 2 + 1], ColGroup<D, N> &G)
+__device__ __forceinline__ void group_gather(const uint32_t (&w)[N][(D + 1) / 2 + 1], ColGroup<D, N> &G, uint32_t win)
 {
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            G.addr[j][k] = (k & 1) ? ((w[j][k >> 1] >> 14) & 0x3FFFCu) : ((w[j][k >> 1] << 2) & 0x3FFFCu);
+            G.addr[j][k] = ((k & 1) ? ((w[j][k >> 1] >> 14) & 0x3FFFCu) : ((w[j][k >> 1] << 2) & 0x3FFFCu)) | win;
             G.r[j][k] = lds_f32(G.addr[j][k]);
         }
 }
@@ -232,12 +234,12 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
         float acc = 0.f;
         for (int k = 0; k < D; ++k) {
             const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
-            acc += lds_f32((k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu));
+            acc += lds_f32(((k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu)) | c.win);
         }
         const float v = acc + (lane_prior ? __ldg(lane_prior) : __uint_as_float(pri.bits[c.t4 >> 2]));
         for (int k = 0; k < D; ++k) {
             const uint32_t w = lds_u32(c.ix + edge_idx_off(H, k >> 1, c.lane) * 4);
-            const uint32_t addr = (k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu);
+            const uint32_t addr = ((k & 1) ? ((w >> 14) & 0x3FFFCu) : ((w << 2) & 0x3FFFCu)) | c.win;
             const float q = v - lds_f32(addr);
             sts_f32(addr, (q != q) ? 0.f : q);
         }
@@ -267,7 +269,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
         uint32_t w[N][(D + 1) / 2 + 1];
         ColGroup<D, N> G;
         group_load_idx<D, N>(c, 0, w);
-        group_gather<D, N>(w, G);
+        group_gather<D, N>(w, G, c.win);
         group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
     }
     if constexpr (N == 2) {
@@ -275,7 +277,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
             uint32_t w[1][(D + 1) / 2 + 1];
             ColGroup<D, 1> G;
             group_load_idx<D, 1>(c, 0, w);
-            group_gather<D, 1>(w, G);
+            group_gather<D, 1>(w, G, c.win);
             group_finish<D, EXACT, WRITE_V, 1>(c, G, pri);
         }
     }

@@ -690,6 +690,7 @@ int launch_minsum(qb_decoder *dec, const MinsumLaunch &a, cudaStream_t st)
         return launch_minsum_edge_h2(dec, dec->edge, dec->edge_h2, a, st);
     }
     if (a.damping == 1.0f && dec->edge && a.max_iter > 0) return launch_minsum_edge(dec, dec->edge, a, st);
+    if (a.damping == 1.0f && dec->cluster && a.max_iter > 0) return launch_minsum_cluster(dec, dec->cluster, a, st);
     const int S = (a.damping == 1.0f) ? fast_shots_per_cta(dec) : 0;
     if (S == 4) return launch_fast<4>(dec, a, st);
     if (S == 2) return launch_fast<2>(dec, a, st);

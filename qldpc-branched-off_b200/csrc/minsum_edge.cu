@@ -161,6 +161,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.vid = eg.var_id + c0 * 32 + lane;
             c.vid_next = write_v ? __ldg(c.vid) : 0u;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
+            c.win = 0u;
 #ifndef QB_EDGE_SKIP_B
             if (write_v) phase_b<true>(c, cls, c1, cmeta, eg.lane_prior, pri);
             else phase_b<false>(c, cls, c1, cmeta, eg.lane_prior, pri);

@@ -603,6 +603,50 @@ def test_edge_kernel_matches_compressed_state_kernel_and_oracle_on_random_graphs
                 assert np.array_equal(oh, h0[i])
 
 
+# ---- per-edge min-sum on a thread-block cluster ([[288,12,18]]: the graph does not fit one SM) -----------------------------
+@pytest.mark.parametrize("p,max_iter", [(0.001, 20), (0.003, 20), (0.006, 12)])
+def test_cluster_kernel_288_matches_compressed_state_kernel_and_oracle(p, max_iter):
+    """minsum_edge_cluster.cu against the compressed-state kernel (same float32 recurrence, both add in row order: equal
+    hard decisions, flags, iteration counts; posteriors to the last bits) and against the float64 oracle on the sides
+    both arithmetics converge on.  Low p: nearly every side converges (early exit, exact parity over the cluster)."""
+    s = code_setup("288"); M = matrices("288", p)
+    smp = _lib.Sampler(s["ft"])
+    B = 192
+    szb, _, sxb, _, _ = smp.sample(77, 0, B, p)
+    smp.close()
+    for sd, bits in (("Z", szb), ("X", sxb)):
+        H = np.asarray(M["Hdec" + sd]) & 1; m, n = H.shape
+        Hc = csr_matrix(H); prior = orc.llr_priors(M["channel_probs" + sd])
+        syn = unpack(bits.view(np.uint8), m).astype(np.int8)
+        outs = []
+        for no_cluster in ("", "1"):
+            if not no_cluster:
+                os.environ["QLDPC_B200_CLUSTER"] = "1"       # opt-in: the compressed-state kernel is the (faster) default
+            try:
+                dec = _lib.Decoder(Hc.indptr, Hc.indices, n, prior)
+                path = dec.minsum_path()
+                assert (path == 0) if no_cluster else (path >= 2), path
+                outs.append(dec.minsum(syn, max_iter, _lib.QB_ALPHA_DYNAMIC))
+                if not no_cluster:       # a second call on the same handle (shot counter, cleared outputs)
+                    again = dec.minsum(syn, max_iter, _lib.QB_ALPHA_DYNAMIC)
+                    for a_, b_ in zip(again, outs[0]):
+                        assert np.array_equal(a_, b_, equal_nan=True)
+                dec.close()
+            finally:
+                os.environ.pop("QLDPC_B200_CLUSTER", None)
+        (h0, c0, v0, f0), (h1, c1, v1, f1) = outs
+        assert np.array_equal(c0, c1) and np.array_equal(f0, f1), (np.flatnonzero(c0 != c1), np.flatnonzero(f0 != f1))
+        assert np.array_equal(h0, h1)
+        np.testing.assert_allclose(v0, v1, rtol=1e-6, atol=1e-6)
+        if p <= 0.001:
+            assert c0.mean() > 0.5
+        for i in range(0, B, 16):
+            oh, oc, ov, of = orc.performMinSum_Symmetric_Sparse(Hc, syn[i], prior, maxIter=max_iter)
+            assert oc == c0[i] and of == f0[i]
+            if oc:
+                assert np.array_equal(oh, h0[i])
+
+
 # ---- SCOPT beta pre-pass (reference scopt.py) on the GPU decoder -----------------------------------------------------
 def test_scopt_beta_vs_reference_golden_and_run_simulation():
     """The batched float32 GPU decoder behind estimate_scopt_beta gives the reference's beta for the same seeded generator
