@@ -275,7 +275,17 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
         const int M = ws >= 0 ? P.ncand2[ws] : P.ncand[q];
         int why = M < 0 ? 4 : -1;                                // >= 0: overflow, CNT_STAT + why counts the reason
         int R = 0, t = 0, off = 0;
+#ifdef QB_OSD_STATS
+        int st_blocks = 0, st_hitblocks = 0, st_rows = 0, st_cands = 0;
+        const long long st_t0 = clock64();
+#endif
         uint32_t ul = 0u, sl = 0u;                               // lanes < WV: slots in use / transformed syndrome, word `lane`
+        // lane l: OR of the vectors of compact rows 32 l .. 32 l + 31 (a superset: bits cancelled by an update stay until
+        // their slot is the pivot).  Measured on the gross code: a pivot's slot is present in 1.5 of the 5.4 blocks of 32
+        // rows a side has touched, so the update sweep visits only the blocks whose summary has the bit.
+        uint32_t sum[WV];
+#pragma unroll
+        for (int j = 0; j < WV; ++j) sum[j] = 0u;
         bool finished = false;
         if (why < 0) {
             // ---- reset the row map, then compact rows / slots 0 .. wt-1 for the support of the residual syndrome ----
@@ -315,6 +325,9 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
                 const int lo = 32 * lane;
                 const uint32_t msk = R >= lo + 32 ? 0xFFFFFFFFu : (R > lo ? (1u << (R - lo)) - 1u : 0u);
                 ul = lane < WV ? msk : 0xFFFFFFFFu; sl = lane < WV ? msk : 0u;
+                // rows 0 .. R-1 start as unit vectors on slots 0 .. R-1: block `lane` uses exactly word `lane`
+#pragma unroll
+                for (int j = 0; j < WV; ++j) sum[j] = j == lane ? msk : 0u;
             }
             finished = R == 0;
             __syncwarp();
@@ -339,16 +352,24 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             const uint16_t *sigp = sig16 + k_of_lane;
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i, sigp += 8) {
+#ifdef QB_OSD_STATS
+                ++st_cands;
+#endif
                 // ---- v = XOR of the vectors of the candidate's rows (gather layout: k = row slot, w = word) ----
-                uint32_t val = 0u;
+                // A row seen for the first time would get the next compact row and a unit vector on a new slot.  The FIRST
+                // such row of a candidate needs no slot: the candidate is then certainly a pivot (nothing else has that
+                // bit), the new row itself can serve as the pivot row, and eliminating with it changes no other vector --
+                // the new compact row simply starts with v (the XOR of the candidate's other rows) and is the frozen row.
+                uint32_t val = 0u, vpr = 0xFFFFFFFFu;
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const uint32_t r = sigp[ps * KP];
                     const bool valid = r != 0xFFFFu;
-                    uint32_t x = valid ? (uint32_t)rowmap[r] : 0u;
+                    uint32_t x = valid ? (uint32_t)rowmap[r] : 0xFFFFu;
                     uint32_t fresh = __ballot_sync(0xFFFFFFFFu, valid && x == 0xFFFFu && w_of_lane == 0);
-                    if (fresh) {                                 // rows seen for the first time: next compact row, lowest unused slot
-                        do {
+                    if (fresh) {
+                        if (vpr == 0xFFFFFFFFu) { const int src = __ffs(fresh) - 1; fresh &= fresh - 1; vpr = __shfl_sync(0xFFFFFFFFu, r, src); }
+                        while (fresh) {                          // further new rows: next compact row, lowest unused slot
                             const int src = __ffs(fresh) - 1; fresh &= fresh - 1;
                             const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, src);
                             const uint32_t um = __ballot_sync(0xFFFFFFFFu, ul != 0xFFFFFFFFu);
@@ -360,17 +381,31 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
                             if (lane == wj) ul |= fbit;
                             if (lane == 0) rowmap[rr] = (uint16_t)R;
                             if (lane < WV) Tw[R * WV + lane] = lane == wj ? fbit : 0u;
+#pragma unroll
+                            for (int j = 0; j < WV; ++j) if (j == wj && lane == (R >> 5)) sum[j] |= fbit;
                             ++R;
-                        } while (fresh);
+                        }
                         if (why >= 0) break;
                         __syncwarp();
-                        if (valid && x == 0xFFFFu) x = rowmap[r];
+                        if (valid && x == 0xFFFFu) x = rowmap[r];                 // (stays 0xFFFF for the pivot row)
                     }
-                    if (valid && w_of_lane < WV) val ^= Tw[x * WV + w_of_lane];
+                    if (x != 0xFFFFu && w_of_lane < WV) val ^= Tw[x * WV + w_of_lane];
                 }
                 if (why >= 0) break;
 #pragma unroll
                 for (int o = LV; o < 32; o <<= 1) val ^= __shfl_xor_sync(0xFFFFFFFFu, val, o);
+                if (vpr != 0xFFFFFFFFu) {
+                    if (R >= Tr.rcap) { why = 1; break; }
+                    if (off + 1 > Tr.rec_cap || t >= Tr.rcap) { why = 3; break; }
+                    if (lane < WV) Tw[R * WV + lane] = val;
+#pragma unroll
+                    for (int j = 0; j < WV; ++j) { const uint32_t wjv = __shfl_sync(0xFFFFFFFFu, val, j); if (lane == (R >> 5)) sum[j] |= wjv; }
+                    const uint32_t col_id = __shfl_sync(0xFFFFFFFFu, idx_batch, i);
+                    if (lane == 0) { rowmap[vpr] = (uint16_t)R; rec[off] = (uint32_t)R; meta[t] = col_id; }   // unit record: sigma = 0, word count 0
+                    off += 1; ++t; ++R;
+                    __syncwarp();
+                    continue;
+                }
                 const uint32_t nz = __ballot_sync(0xFFFFFFFFu, val != 0u) & WVMASK;
                 if (nz == 0u) continue;                          // dependent on the pivots so far
                 // ---- pivot: slot b = lowest set bit of v ----
@@ -412,9 +447,29 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
                     return __ballot_sync(0xFFFFFFFFu, has);
                 };
                 const int nb1 = min(nblk, 32);
-#pragma unroll 2
-                for (int blk = 0; blk < nb1; ++blk) { const uint32_t flags = scan_block(blk); if (blk == lane) myflags = flags; }
-                for (int blk = 32; blk < nblk; ++blk) {                      // (more than 1024 touched rows)
+                uint32_t sw = 0u;
+#pragma unroll
+                for (int j = 0; j < WV; ++j) sw = j == wsel ? sum[j] : sw;
+                uint32_t need = __ballot_sync(0xFFFFFFFFu, (sw & bmask) != 0u && lane < nb1);
+                while (need) {
+                    const int blk = __ffs(need) - 1; need &= need - 1;
+                    tp = T4 + (size_t)(blk * 32 + lane) * Q;
+                    const uint32_t flags = scan_block(blk);
+                    if (blk == lane) {
+                        myflags = flags;
+                        if (flags) {
+#pragma unroll
+                            for (int qq = 0; qq < Q; ++qq) { sum[4 * qq] |= v4[qq].x; sum[4 * qq + 1] |= v4[qq].y; sum[4 * qq + 2] |= v4[qq].z; sum[4 * qq + 3] |= v4[qq].w; }
+                        }
+                    }
+#ifdef QB_OSD_STATS
+                    ++st_blocks; st_hitblocks += flags != 0u; st_rows += __popc(flags);
+#endif
+                }
+#pragma unroll
+                for (int j = 0; j < WV; ++j) sum[j] &= ~bm[j];                   // bit b is clear in every row now
+                tp = T4 + (size_t)(32 * 32 + lane) * Q;
+                for (int blk = 32; blk < nblk; ++blk) {                      // (more than 1024 touched rows: always visited)
                     const uint32_t flags = scan_block(blk);
                     if (lane == 0) rec[off + blk] = flags;
                 }
@@ -447,8 +502,9 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
         __syncwarp();
         uint32_t *hard_rw = P.a.hard_bits + (size_t)shot * g.nw;
         uint32_t mtA = t > 0 ? ldcg_u32(&meta[t - 1]) : 0u, mtB = t > 1 ? ldcg_u32(&meta[t - 2]) : 0u;
-        int offA = off - (int)(mtA >> 17);
-        uint32_t recA = (t > 0 && lane < (int)(mtA >> 17)) ? ldcg_u32(&rec[offA + lane]) : 0u;
+        // (a pivot made by a new row has a unit record: word count 0 in meta, one record word = the compact row)
+        int offA = off - max((int)(mtA >> 17), 1);
+        uint32_t recA = (t > 0 && lane < max((int)(mtA >> 17), 1)) ? ldcg_u32(&rec[offA + lane]) : 0u;
         uint32_t sigA = (t > 0 && lane < 8) ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
         for (int tt = t - 1; tt >= 0; --tt) {
             const uint32_t mt = mtA, recw = recA, r = sigA;
@@ -457,7 +513,7 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             mtA = mtB;
             mtB = tt >= 2 ? ldcg_u32(&meta[tt - 2]) : 0u;
             if (tt >= 1) {
-                const int nwa = (int)(mtA >> 17);
+                const int nwa = max((int)(mtA >> 17), 1);
                 offA = offc - nwa;
                 recA = lane < nwa ? ldcg_u32(&rec[offA + lane]) : 0u;
                 sigA = lane < 8 ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
@@ -465,6 +521,7 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             uint32_t par = lane < nwr ? (uint32_t)__popc(recw & ybits[lane]) : 0u;
             for (int w = 32 + lane; w < nwr; w += 32) par ^= (uint32_t)__popc(ldcg_u32(&rec[offc + w]) & ybits[w]);
             par = __reduce_xor_sync(0xFFFFFFFFu, par) & 1u;
+            if (nwr == 0) { const uint32_t x = __shfl_sync(0xFFFFFFFFu, recw, 0); par = (ybits[x >> 5] >> (x & 31)) & 1u; }
             if ((((mt >> 16) & 1u) ^ par) != 0u) {
                 if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
                 if (r != 0xFFFFu) { const uint32_t x = rowmap[r]; atomicXor(&ybits[x >> 5], 1u << (x & 31)); }
@@ -472,6 +529,19 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             }
         }
         if (P.a.rank_out && lane == 0) P.a.rank_out[shot] = t | (1 << 16);
+#ifdef QB_OSD_STATS
+        if (lane == 0) {
+            atomicAdd(&P.counters[32], 1); atomicAdd(&P.counters[33], t); atomicAdd(&P.counters[34], st_blocks);
+            atomicAdd(&P.counters[35], st_hitblocks); atomicAdd(&P.counters[36], st_rows); atomicAdd(&P.counters[37], st_cands);
+            atomicAdd(&P.counters[38], R);
+            // slowest side of the tier: cycles (in units of 256), its pivots / candidates / rows
+            const int cyc = (int)((clock64() - st_t0) >> 8);
+            int *mx = &P.counters[Tr.out_shots ? 44 : 40];
+            if (atomicMax(&mx[0], cyc) < cyc) { mx[1] = t; mx[2] = st_cands; mx[3] = R; }
+            atomicAdd(&P.counters[Tr.out_shots ? 49 : 48], 1);
+            atomicAdd(&P.counters[Tr.out_shots ? 51 : 50], cyc);
+        }
+#endif
         __syncwarp();
     }
 }
@@ -615,6 +685,18 @@ int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d,
 
 // statistics of the free-row path since the last call: sides that left tier A (out[0..4]) / tier B (out[5..9], these go to
 // the full-width kernel) because of {window exhausted, touched rows, free slots, record buffer, not materialised}
+#ifdef QB_OSD_STATS
+extern "C" int qb_debug_osd_work(qb_decoder *dec, int32_t *out8)
+{
+    if (!dec->ovf.ptr) return -1;
+    cudaDeviceSynchronize();
+    int32_t *c = dec->ovf.as<int32_t>() + 32;
+    if (cudaMemcpy(out8, c, 24 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    cudaMemset(c, 0, 24 * sizeof(int32_t));
+    return 0;
+}
+#endif
+
 int osd_free_stats(qb_decoder *dec, int32_t *out10)
 {
     for (int i = 0; i < 10; ++i) out10[i] = 0;
