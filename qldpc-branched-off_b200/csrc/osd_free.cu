@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         __syncthreads();
         const int qi = s_q;
         if (qi >= n_in) break;
+#ifdef QB_OSD_STATS
+        const long long sp0 = clock64();
+#endif
         const int q = P.sel_q ? P.sel_q[qi] : qi;
         const int shot = P.a.fail_idx ? P.a.fail_idx[q] : q;
         const uint32_t *hard = P.a.hard_bits + (size_t)shot * g.nw;
@@ -139,6 +142,9 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
             for (int u = 0; u < 8; ++u) if (kb[u] != 0xFFFFFFFFu) atomicAdd(&hist[kb[u]], 1u);
         }
         __syncthreads();
+#ifdef QB_OSD_STATS
+        const long long sp1 = clock64();
+#endif
         {   // weight of the residual: sizes the window (the candidates an elimination examines grow with it)
             int wt = 0;
             for (int w = tid; w < mw; w += SELF_THREADS) { const uint32_t x = sv[w]; wt += __popc(x); P.res[(size_t)q * mw + w] = x; }
@@ -188,6 +194,9 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
             __syncthreads();
             continue;
         }
+#ifdef QB_OSD_STATS
+        const long long sp2 = clock64();
+#endif
         // ---- scatter (unordered inside a bin), then rank inside each bin by (key, index) ----
         for (int j0 = tid; j0 < n; j0 += 8 * SELF_THREADS) {
             uint32_t kb[8];
@@ -205,6 +214,9 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
             }
         }
         __syncthreads();
+#ifdef QB_OSD_STATS
+        const long long sp3 = clock64();
+#endif
         uint16_t *out = P.cand + (size_t)oi * P.cap;
         for (int i = tid; i < M; i += SELF_THREADS) {
             const uint32_t key = listK[i];
@@ -221,6 +233,14 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         }
         if (tid == 0) { P.ncand[oi] = M; if (second) P.win_slot[q] = qi; }
         __syncthreads();
+#ifdef QB_OSD_STATS
+        if (tid == 0) {
+            const long long sp4 = clock64();
+            int *c = &P.counters[second ? 58 : 52];
+            atomicAdd(&c[0], 1); atomicAdd(&c[1], (int)((sp1 - sp0) >> 8)); atomicAdd(&c[2], (int)((sp2 - sp1) >> 8));
+            atomicAdd(&c[3], (int)((sp3 - sp2) >> 8)); atomicAdd(&c[4], (int)((sp4 - sp3) >> 8)); atomicAdd(&c[5], M);
+        }
+#endif
     }
 }
 
@@ -586,6 +606,7 @@ static bool free_plan(const qb_decoder *dec, FreePlan &pl)
     if (!tier_plan(dec, big ? 3 : 2, rcapB, warpsB, pl.B)) return false;
     pl.max_wt = 128 * pl.B.Q;
     pl.cap2 = (g.n + 31) & ~31;                                              // second pass: all columns
+    if (const char *e = getenv("QLDPC_B200_OSD_CAP2")) { const int v = atoi(e); if (v >= 256) pl.cap2 = std::min(pl.cap2, v & ~31); }
     pl.smem_sel = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap * (4 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
     pl.smem_sel2 = sizeof(uint32_t) * SELF_BINS + (size_t)pl.cap2 * (4 + 2) + sizeof(uint32_t) * (size_t)g.mw + 16;
     return pl.smem_sel + 1024 <= (size_t)dec->max_smem_optin && pl.smem_sel2 + 1024 <= (size_t)dec->max_smem_optin;
@@ -691,8 +712,8 @@ extern "C" int qb_debug_osd_work(qb_decoder *dec, int32_t *out8)
     if (!dec->ovf.ptr) return -1;
     cudaDeviceSynchronize();
     int32_t *c = dec->ovf.as<int32_t>() + 32;
-    if (cudaMemcpy(out8, c, 24 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-    cudaMemset(c, 0, 24 * sizeof(int32_t));
+    if (cudaMemcpy(out8, c, 32 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    cudaMemset(c, 0, 32 * sizeof(int32_t));
     return 0;
 }
 #endif
