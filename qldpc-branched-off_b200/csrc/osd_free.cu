@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             __syncwarp();
         }
 
+#ifdef QB_OSD_STATS
+        const long long st_t1 = clock64();
+#endif
         // ---- candidates in reliability order, 32 at a time (ids and signatures prefetched one batch ahead) ----
         const uint16_t *cand = ws >= 0 ? P.cand2 + (size_t)ws * P.cap2 : P.cand + (size_t)q * P.cap;
         uint32_t idx_cur = 0xFFFFu, idx_nxt = 0xFFFFu;
@@ -517,36 +520,54 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             }
             continue;
         }
-        // ---- back substitution over the frozen rows, last pivot first (records prefetched one pivot ahead) ----
+#ifdef QB_OSD_STATS
+        const long long st_t2 = clock64();
+#endif
+        // ---- back substitution over the frozen rows, last pivot first ----
+        // 32 pivots at a time: their meta words, records and column signatures are fetched from L2 with three rounds of
+        // coalesced loads (the dependent chain e_t -> y -> e_(t-1) then runs from shared memory: one L2 round trip per pivot
+        // was 30 % of a side's time).  The records are staged in the T buffer, which is dead by now; a chunk holds at most
+        // 32 * rcap / 32 = rcap words, T has 4 Q rcap.
         for (int w = lane; w < (R + 31) >> 5; w += 32) ybits[w] = 0u;
-        __syncwarp();
         uint32_t *hard_rw = P.a.hard_bits + (size_t)shot * g.nw;
-        uint32_t mtA = t > 0 ? ldcg_u32(&meta[t - 1]) : 0u, mtB = t > 1 ? ldcg_u32(&meta[t - 2]) : 0u;
-        // (a pivot made by a new row has a unit record: word count 0 in meta, one record word = the compact row)
-        int offA = off - max((int)(mtA >> 17), 1);
-        uint32_t recA = (t > 0 && lane < max((int)(mtA >> 17), 1)) ? ldcg_u32(&rec[offA + lane]) : 0u;
-        uint32_t sigA = (t > 0 && lane < 8) ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
-        for (int tt = t - 1; tt >= 0; --tt) {
-            const uint32_t mt = mtA, recw = recA, r = sigA;
-            const int offc = offA;
-            const int nwr = (int)(mt >> 17), col = (int)(mt & 0xFFFFu);
-            mtA = mtB;
-            mtB = tt >= 2 ? ldcg_u32(&meta[tt - 2]) : 0u;
-            if (tt >= 1) {
-                const int nwa = max((int)(mtA >> 17), 1);
-                offA = offc - nwa;
-                recA = lane < nwa ? ldcg_u32(&rec[offA + lane]) : 0u;
-                sigA = lane < 8 ? (uint32_t)__ldg(colsig16 + (size_t)(mtA & 0xFFFFu) * 8 + lane) : 0xFFFFu;
+        uint32_t *stage = Tw;
+        int off_hi = off;
+        for (int hi_t = t; hi_t > 0; hi_t -= 32) {
+            const int nch = min(32, hi_t);
+            const uint32_t mt_l = lane < nch ? ldcg_u32(&meta[hi_t - 1 - lane]) : 0u;          // lane j: pivot hi_t - 1 - j
+            // (a pivot made by a new row has a unit record: word count 0 in meta, one record word = the compact row)
+            const int cnt_l = lane < nch ? max((int)(mt_l >> 17), 1) : 0;
+            int inc = cnt_l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+            const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const int off_lo = off_hi - total;
+            const int start_l = total - inc;                                                     // offset of the lane's record inside the chunk
+            __syncwarp();
+            for (int w = lane; w < total; w += 32) stage[w] = ldcg_u32(&rec[off_lo + w]);
+            sigbuf[lane] = lane < nch ? g.colsig[mt_l & 0xFFFFu] : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            __syncwarp();
+            for (int j = 0; j < nch; ++j) {
+                const uint32_t mt = __shfl_sync(0xFFFFFFFFu, mt_l, j);
+                const int st0 = __shfl_sync(0xFFFFFFFFu, start_l, j);
+                const int nwr = (int)(mt >> 17), col = (int)(mt & 0xFFFFu);
+                uint32_t par;
+                if (nwr == 0) {
+                    const uint32_t x = stage[st0];
+                    par = (ybits[x >> 5] >> (x & 31)) & 1u;
+                } else {
+                    par = lane < nwr ? (uint32_t)__popc(stage[st0 + lane] & ybits[lane]) : 0u;
+                    for (int w = 32 + lane; w < nwr; w += 32) par ^= (uint32_t)__popc(stage[st0 + w] & ybits[w]);
+                    par = __reduce_xor_sync(0xFFFFFFFFu, par) & 1u;
+                }
+                if ((((mt >> 16) & 1u) ^ par) != 0u) {
+                    if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
+                    const uint32_t r = lane < 8 ? (uint32_t)sig16[j * 8 + lane] : 0xFFFFu;
+                    if (r != 0xFFFFu) { const uint32_t x = rowmap[r]; atomicXor(&ybits[x >> 5], 1u << (x & 31)); }
+                    __syncwarp();
+                }
             }
-            uint32_t par = lane < nwr ? (uint32_t)__popc(recw & ybits[lane]) : 0u;
-            for (int w = 32 + lane; w < nwr; w += 32) par ^= (uint32_t)__popc(ldcg_u32(&rec[offc + w]) & ybits[w]);
-            par = __reduce_xor_sync(0xFFFFFFFFu, par) & 1u;
-            if (nwr == 0) { const uint32_t x = __shfl_sync(0xFFFFFFFFu, recw, 0); par = (ybits[x >> 5] >> (x & 31)) & 1u; }
-            if ((((mt >> 16) & 1u) ^ par) != 0u) {
-                if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
-                if (r != 0xFFFFu) { const uint32_t x = rowmap[r]; atomicXor(&ybits[x >> 5], 1u << (x & 31)); }
-                __syncwarp();
-            }
+            off_hi = off_lo;
         }
         if (P.a.rank_out && lane == 0) P.a.rank_out[shot] = t | (1 << 16);
 #ifdef QB_OSD_STATS
@@ -560,6 +581,7 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             if (atomicMax(&mx[0], cyc) < cyc) { mx[1] = t; mx[2] = st_cands; mx[3] = R; }
             atomicAdd(&P.counters[Tr.out_shots ? 49 : 48], 1);
             atomicAdd(&P.counters[Tr.out_shots ? 51 : 50], cyc);
+            if (!Tr.out_shots) { atomicAdd(&P.counters[39], (int)((st_t1 - st_t0) >> 8)); atomicAdd(&P.counters[64], (int)((st_t2 - st_t1) >> 8)); }
         }
 #endif
         __syncwarp();
@@ -652,13 +674,13 @@ int launch_osd0_free(qb_decoder *dec, const OsdLaunch &a, int32_t **ovf_count_d,
     // sides the second selection pass has buffers for: 1/8 of the queue where 1-4 % leave tier A (m <= 1536; gross code
     // 1.1 % at p = 0.005, 3.6 % at p = 0.006), 1/4 for the large codes (the [[288,12,18]] code at p = 0.006: 12 %)
     const size_t F2 = std::max<size_t>(64, g.m <= 1536 ? F / 8 : F / 4);
-    const size_t need = 256 + al(F * pl.cap * 2) + al(F * 4) + al(F * g.mw * 4) + al(slotsA * pl.A.rec_cap * 4) + al(slotsA * pl.A.rcap * 4) +
+    const size_t need = 512 + al(F * pl.cap * 2) + al(F * 4) + al(F * g.mw * 4) + al(slotsA * pl.A.rec_cap * 4) + al(slotsA * pl.A.rcap * 4) +
                         al(slotsB * pl.B.rec_cap * 4) + al(slotsB * pl.B.rcap * 4) + 4 * al(F * 4) + al(F2 * pl.cap2 * 2) + al(F2 * 4);
     const bool grown = dec->ovf.cap < need;
     if (int rc = dec->ovf.ensure(need)) return rc;
     unsigned char *p = dec->ovf.as<unsigned char>();
-    if (grown) QB_CUDA(cudaMemsetAsync(p, 0, 256, st));
-    P.counters = reinterpret_cast<int32_t *>(p); p += 256;
+    if (grown) QB_CUDA(cudaMemsetAsync(p, 0, 512, st));
+    P.counters = reinterpret_cast<int32_t *>(p); p += 512;
     P.cand = reinterpret_cast<uint16_t *>(p); p += al(F * pl.cap * 2);
     P.ncand = reinterpret_cast<int32_t *>(p); p += al(F * 4);
     P.res = reinterpret_cast<uint32_t *>(p); p += al(F * g.mw * 4);
@@ -712,8 +734,8 @@ extern "C" int qb_debug_osd_work(qb_decoder *dec, int32_t *out8)
     if (!dec->ovf.ptr) return -1;
     cudaDeviceSynchronize();
     int32_t *c = dec->ovf.as<int32_t>() + 32;
-    if (cudaMemcpy(out8, c, 32 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-    cudaMemset(c, 0, 32 * sizeof(int32_t));
+    if (cudaMemcpy(out8, c, 40 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    cudaMemset(c, 0, 40 * sizeof(int32_t));
     return 0;
 }
 #endif

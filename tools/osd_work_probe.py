@@ -14,7 +14,7 @@ counts, _ = eng.pipeline.run(1234, 0, B, p, cfg)
 print(counts.tolist(), eng.pipeline.stats())
 lib = _lib.load()
 for nm, dec in (("Z", eng.decZ), ("X", eng.decX)):
-    out = np.zeros(32, np.int32)
+    out = np.zeros(40, np.int32)
     rc = lib.qb_debug_osd_work(dec._h, out.ctypes.data_as(C.c_void_p))
     sides, piv, blocks, hitb, rows, cands, R = [int(x) for x in out[:7]]
     print(nm, "rc", rc, "sides", sides, "| per side: pivots %.1f candidates %.1f touched rows %.1f | per pivot: blocks scanned %.2f, blocks with a hit %.2f, rows updated %.2f"
@@ -25,3 +25,4 @@ for nm, dec in (("Z", eng.decZ), ("X", eng.decX)):
         k = max(1, int(out[o]))
         print("   ", nm2, "sides", int(out[o]), "| k-cycles per side: residual+histogram %.1f, window scan %.1f, scatter %.1f, rank+write %.1f | candidates written %.0f"
               % tuple([out[o + i] * 0.256 / k for i in (1, 2, 3, 4)] + [out[o + 5] / k]))
+    print("    tier A phases, k-cycles per side: setup %.1f, candidate loop %.1f, back substitution %.1f" % (out[7] * 0.256 / max(1, out[16]), out[32] * 0.256 / max(1, out[16]), (out[18] - out[7] - out[32]) * 0.256 / max(1, out[16])))
