@@ -271,19 +271,23 @@ def main():
     big_ev = torch.empty(base, dtype=torch.int32).pin_memory(); big_ev.numpy()[:] = np.concatenate(ev_parts)
     pflags = torch.empty(e2e_steps * Be, dtype=torch.uint8).pin_memory()
     eng.pipeline.set_stream(None)
-    for i in range(2):
-        eng.pipeline.run_events(sets[i % n_sets][0].numpy(), sets[i % n_sets][1].numpy().view(np.uint32), cfg, flags_out=pflags.numpy()[:Be])
-    barrier()
-    t0 = time.perf_counter()
+    # one untimed call of the same size first (the library sizes its device-side event buffer on the first call of a
+    # size), then three timed calls, each bracketed by barrier + synchronize; the median is reported (a single wall-clock
+    # sample of a ~0.5 s host call was seen to vary 2x with host noise), all three are listed in e2e.samples
     eng.pipeline.run_events(big_ptr.numpy(), big_ev.numpy().view(np.uint32), cfg, flags_out=pflags.numpy())
     h2d = big_ptr.numel() * 4 + big_ev.numel() * 4
     d2h = e2e_steps * Be + 64
-    barrier()
-    te = time.perf_counter() - t0
-    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * e2e_steps / float(te_t.item())
+    e2e_samples = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        eng.pipeline.run_events(big_ptr.numpy(), big_ev.numpy().view(np.uint32), cfg, flags_out=pflags.numpy())
+        barrier()
+        te_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        e2e_samples.append(world * Be * e2e_steps / float(te_t.item()))
+    e2e_value = sorted(e2e_samples)[1]
 
     # ---- e2e through the public entry point a user of the reference calls: run_simulation(num_trials=2**20, ...) ----
     # wall clock of the whole call on this rank's GPU: host table build (fault signatures, priors), handle creation,
@@ -356,7 +360,7 @@ def main():
                              "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
                              "note": "non-binding by design: messages never leave the SM; traffic = algorithmic bytes (posteriors of non-converged sides), no re-reads"},
             "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-                    "shots_per_step": Be, "steps": e2e_steps,
+                    "shots_per_step": Be, "steps": e2e_steps, "samples": e2e_samples, "statistic": "median of 3 timed calls after one untimed call of the same size",
                     "path": "one qb_pipeline_run_events_host call (the C-ABI entry behind run_trial_fast + the decoders) over all steps: fault "
                             "events sampled on the host BEFORE the timed region (three sets, tiled, pinned) -> one H2D -> per batch K2 syndromes -> "
                             "min-sum -> OSD-0 -> logical check -> flags D2H (pinned); contains no sampling work; wall clock incl. the final host sync"},

@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
     const int n_in = Tr.in_count ? min(*Tr.in_count, F) : F;
     const int mw = g.mw;
     const int k_of_lane = lane / LV, w_of_lane = lane % LV;
-    const uint16_t *colsig16 = reinterpret_cast<const uint16_t *>(g.colsig);
 
     while (true) {
         int qi = 0;

@@ -19,7 +19,7 @@ M = matrices_from_tables(ft, p, d)
 eng = ShotEngine(cc, code["Lx"], code["Lz"], M, max_batch=B)
 res = {}
 for it in (10, 20, 40):
-    cfg = _lib.make_config(it, _lib.QB_ALPHA_DYNAMIC)
+    cfg = _lib.make_config(it, _lib.QB_ALPHA_DYNAMIC, use_osd=False)
     eng.pipeline.run(1, 0, B, p, cfg)
     eng.pipeline.run(1234, 0, B, p, cfg)
     st = eng.pipeline.stats()
