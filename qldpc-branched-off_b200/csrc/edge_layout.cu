@@ -340,6 +340,15 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                     L.col_idx[cs_base[t] + edge_idx_off(H, kk, l)] = slot | (slot << 16);
                 }
         }
+        // odd degree: the upper half of a lane's last index word is free and carries 0xFF00 | the variable's 8-bit
+        // fingerprint (EDGE_SIG_TAG: above every slot index), so the float32 kernel needs no separate fingerprint load
+        if (csl[t].deg & 1) {
+            const int H = (csl[t].deg + 1) / 2;
+            for (int l = 0; l < 32; ++l) {
+                uint32_t &wi = L.col_idx[cs_base[t] + edge_idx_off(H, H - 1, l)];
+                wi = (wi & 0x0000FFFFu) | ((EDGE_SIG_TAG | (l < nl ? (L.col_sig[t * 32 + l] & 0xFFu) : 0u)) << 16);
+            }
+        }
     }
     L.ok = true;
     return L;

@@ -134,8 +134,9 @@ __device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int bas
 struct ColCtx {
     uint32_t ix;            // shared address of the index block of the next task
     uint32_t lane4, lane8;
-    uint32_t sg;            // shared address of the 8-bit fingerprint of the next task's lane variable
+    uint32_t sg;            // shared address of the 8-bit fingerprint of the lane's variable in slice 0 (slice t: + 32 t = + 8 t4)
     uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
+    uint32_t fpw;           // same for the variables whose fingerprint sits in the upper half of an index word (SIGW): bits 16-23
     uint32_t myhw;          // lane j keeps the hard-decision word of the warp's j-th task
     uint32_t t4;            // 4 * next task: byte offset of its prior, compared with lane_t4 to pick the lane that keeps its hard-decision word
     uint32_t lane_t4;       // 4 * (first task of the warp + lane)
@@ -188,8 +189,10 @@ __device__ __forceinline__ void group_gather(const uint32_t (&w)[N][(D + 1) / 2 
 }
 
 // E holds R on entry and the unclipped v - R on exit (the clamp is applied per row in phase A)
-template <int D, bool EXACT, bool WRITE_V, int N>
-__device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G, const EdgePriors &pri)
+// SIGW: the layout keeps the fingerprint of an odd-degree variable in the free upper half of its last index word
+// (edge_layout.h, EDGE_SIG_TAG), which saves the byte load; c.fp then carries tag bits above bit 7 that the caller masks
+template <int D, bool EXACT, bool WRITE_V, int N, bool SIGW>
+__device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G, const EdgePriors &pri, const uint32_t (&w)[N][(D + 1) / 2 + 1])
 {
     float v[N];
 #pragma unroll
@@ -210,7 +213,8 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const bool neg = v[j] < 0.f;                       // kernels.py:349
-        if (neg) c.fp ^= lds_u8(c.sg + 32 * j);
+        if constexpr (SIGW && (D & 1)) { if (neg) c.fpw ^= w[j][(D + 1) / 2 - 1]; }       // (unshifted: the caller takes bits 16-23)
+        else { if (neg) c.fp ^= lds_u8(c.sg + 8 * c.t4 + 32 * j); }
         const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
         if (c.lane_t4 == c.t4 + 4 * j) c.myhw = hw;
         if constexpr (WRITE_V) {
@@ -221,7 +225,7 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
             if (vid != 0xFFFFu) c.post[vid] = v[j];
         }
     }
-    c.ix += N * ((D + 1) / 2) * 128; c.sg += 32 * N; c.t4 += 4 * N;
+    c.ix += N * ((D + 1) / 2) * 128; c.t4 += 4 * N;
 }
 
 // any slice: partial with a negative prior, per-lane priors, large degree (meta = degree << 16 | lanes << 22)
@@ -244,13 +248,13 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
             sts_f32(addr, (q != q) ? 0.f : q);
         }
         neg = v < 0.f;
-        if (neg) c.fp ^= lds_u8(c.sg);
+        if (neg) c.fp ^= lds_u8(c.sg + 8 * c.t4);
         if (WRITE_V) c.post[c.vid_next] = v;
     }
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
     if (c.lane_t4 == c.t4) c.myhw = hw;
     if (WRITE_V) { c.vid += 32; c.vid_next = __ldg(c.vid); }
-    c.ix += H * 128; c.sg += 32; c.t4 += 4;
+    c.ix += H * 128; c.t4 += 4;
 }
 
 // Groups of N consecutive slices of one class (two slices at a time double the independent gathers in flight).
@@ -259,7 +263,7 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
 #ifndef QB_EDGE_GROUP
 #define QB_EDGE_GROUP 1
 #endif
-template <int D, bool EXACT, bool WRITE_V>
+template <int D, bool EXACT, bool WRITE_V, bool SIGW>
 __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &pri)
 {
     constexpr int N = (D <= 4) ? QB_EDGE_GROUP : 1;
@@ -270,7 +274,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
         ColGroup<D, N> G;
         group_load_idx<D, N>(c, 0, w);
         group_gather<D, N>(w, G, c.win);
-        group_finish<D, EXACT, WRITE_V, N>(c, G, pri);
+        group_finish<D, EXACT, WRITE_V, N, SIGW>(c, G, pri, w);
     }
     if constexpr (N == 2) {
         if (cnt & 1) {
@@ -278,7 +282,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
             ColGroup<D, 1> G;
             group_load_idx<D, 1>(c, 0, w);
             group_gather<D, 1>(w, G, c.win);
-            group_finish<D, EXACT, WRITE_V, 1>(c, G, pri);
+            group_finish<D, EXACT, WRITE_V, 1, SIGW>(c, G, pri, w);
         }
     }
 }
@@ -286,25 +290,25 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
 // The warp's column slices are sorted by class; cls holds the number of slices per class (16 x u8).  (A jump-table
 // dispatch over a per-warp class program and 2-slice / software-pipelined groups were all measured slower: this
 // phase is sensitive to instruction-fetch stalls, the smallest code wins.)
-template <bool WRITE_V>
+template <bool WRITE_V, bool SIGW = false>
 __device__ __forceinline__ void phase_b(ColCtx &c, uint4 cls, int t_end, const uint32_t *cmeta, const float *lane_prior, const EdgePriors &pri)
 {
-    col_class<0, false, WRITE_V>(c, cls.x & 255, pri);
-    col_class<1, false, WRITE_V>(c, (cls.x >> 8) & 255, pri);
-    col_class<2, false, WRITE_V>(c, (cls.x >> 16) & 255, pri);
-    col_class<3, false, WRITE_V>(c, cls.x >> 24, pri);
-    col_class<4, false, WRITE_V>(c, cls.y & 255, pri);
-    col_class<5, false, WRITE_V>(c, (cls.y >> 8) & 255, pri);
-    col_class<6, false, WRITE_V>(c, (cls.y >> 16) & 255, pri);
+    col_class<0, false, WRITE_V, SIGW>(c, cls.x & 255, pri);
+    col_class<1, false, WRITE_V, SIGW>(c, (cls.x >> 8) & 255, pri);
+    col_class<2, false, WRITE_V, SIGW>(c, (cls.x >> 16) & 255, pri);
+    col_class<3, false, WRITE_V, SIGW>(c, cls.x >> 24, pri);
+    col_class<4, false, WRITE_V, SIGW>(c, cls.y & 255, pri);
+    col_class<5, false, WRITE_V, SIGW>(c, (cls.y >> 8) & 255, pri);
+    col_class<6, false, WRITE_V, SIGW>(c, (cls.y >> 16) & 255, pri);
     if (c.t4 >= 4u * (uint32_t)t_end) return;              // the rare classes follow: skip their tests (far jumps)
-    col_class<7, false, WRITE_V>(c, cls.y >> 24, pri);
-    col_class<8, false, WRITE_V>(c, cls.z & 255, pri);
-    col_class<1, true, WRITE_V>(c, (cls.z >> 8) & 255, pri);
-    col_class<2, true, WRITE_V>(c, (cls.z >> 16) & 255, pri);
-    col_class<3, true, WRITE_V>(c, cls.z >> 24, pri);
-    col_class<4, true, WRITE_V>(c, cls.w & 255, pri);
-    col_class<5, true, WRITE_V>(c, (cls.w >> 8) & 255, pri);
-    col_class<6, true, WRITE_V>(c, (cls.w >> 16) & 255, pri);
+    col_class<7, false, WRITE_V, SIGW>(c, cls.y >> 24, pri);
+    col_class<8, false, WRITE_V, SIGW>(c, cls.z & 255, pri);
+    col_class<1, true, WRITE_V, SIGW>(c, (cls.z >> 8) & 255, pri);
+    col_class<2, true, WRITE_V, SIGW>(c, (cls.z >> 16) & 255, pri);
+    col_class<3, true, WRITE_V, SIGW>(c, cls.z >> 24, pri);
+    col_class<4, true, WRITE_V, SIGW>(c, cls.w & 255, pri);
+    col_class<5, true, WRITE_V, SIGW>(c, (cls.w >> 8) & 255, pri);
+    col_class<6, true, WRITE_V, SIGW>(c, (cls.w >> 16) & 255, pri);
     const int ngen = cls.w >> 24;
     for (int i = 0; i < ngen; ++i)
         col_task_generic<WRITE_V>(c, cmeta[c.t4 >> 2], lane_prior ? lane_prior + (c.t4 >> 2) * 32 + c.lane : nullptr, pri);

@@ -74,7 +74,11 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
     // slot indices become absolute shared word addresses (E base folded in), so that a gather address is one
     // shift + one mask away from the packed pair
     const uint32_t e_word = (uint32_t)__cvta_generic_to_shared(E) >> 2;
-    for (int i = tid; i < eg.idx_words; i += THREADS) idx[i] = eg.col_idx[i] + (e_word | (e_word << 16));
+    // (an upper half >= EDGE_SIG_TAG is the fingerprint of an odd-degree variable, not a slot)
+    for (int i = tid; i < eg.idx_words; i += THREADS) {
+        const uint32_t w = eg.col_idx[i];
+        idx[i] = w + ((w >> 16) >= EDGE_SIG_TAG ? e_word : (e_word | (e_word << 16)));
+    }
     for (int i = tid; i < eg.n_csl; i += THREADS) {
         const uint2 d = eg.ctask[i];
         cmeta[i] = d.x;
@@ -155,19 +159,19 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             ColCtx c;
             c.ix = ix0;
             c.lane4 = lane * 4; c.lane8 = lane * 8;
-            c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
-            c.fp = 0u; c.myhw = 0u;
+            c.sg = (uint32_t)__cvta_generic_to_shared(csig + lane);
+            c.fp = 0u; c.fpw = 0u; c.myhw = 0u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
             c.vid_next = write_v ? __ldg(c.vid) : 0u;
             c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
             c.win = 0u;
 #ifndef QB_EDGE_SKIP_B
-            if (write_v) phase_b<true>(c, cls, c1, cmeta, eg.lane_prior, pri);
-            else phase_b<false>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            if (write_v) phase_b<true, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            else phase_b<false, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
 #endif
             if (lane < c1 - c0) hperm[c0 + lane] = c.myhw;
-            const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp);
+            const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp ^ (c.fpw >> 16)) & 0xFFu;   // (bits 8+: tags of the in-word fingerprints)
             if (lane == 0 && fp) atomicXor(&s_fp[it & 1], fp);
             PROF_T(t3);
             __syncthreads();

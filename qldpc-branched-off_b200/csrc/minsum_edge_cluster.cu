@@ -239,8 +239,8 @@ minsum_cluster_kernel(const ClusterRankDev *ranks, const __grid_constant__ Minsu
             ColCtx c;
             c.ix = S.task[warp].ix0;
             c.lane4 = lane * 4; c.lane8 = lane * 8;
-            c.sg = (uint32_t)__cvta_generic_to_shared(csig + c0 * 32 + lane);
-            c.fp = 0u; c.myhw = 0u;
+            c.sg = (uint32_t)__cvta_generic_to_shared(csig + lane);
+            c.fp = 0u; c.fpw = 0u; c.myhw = 0u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
             c.vid_next = write_v ? __ldg(c.vid) : 0u;
