@@ -340,9 +340,9 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
                     L.col_idx[cs_base[t] + edge_idx_off(H, kk, l)] = slot | (slot << 16);
                 }
         }
-        // odd degree: the upper half of a lane's last index word is free and carries 0xFF00 | the variable's 8-bit
-        // fingerprint (EDGE_SIG_TAG: above every slot index), so the float32 kernel needs no separate fingerprint load
-        if (csl[t].deg & 1) {
+        // odd degree on the fast path: the upper half of a lane's last index word is free and carries EDGE_SIG_TAG | the
+        // variable's 8-bit fingerprint, so the float32 kernel needs no separate fingerprint load
+        if ((csl[t].deg & 1) && csl[t].cls != 15) {
             const int H = (csl[t].deg + 1) / 2;
             for (int l = 0; l < 32; ++l) {
                 uint32_t &wi = L.col_idx[cs_base[t] + edge_idx_off(H, H - 1, l)];

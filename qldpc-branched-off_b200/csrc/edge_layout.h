@@ -39,9 +39,10 @@ QB_HD inline int edge_idx_off(int H, int kk, int lane)
     return (kk >> 1) * 64 + ((kk == H - 1 && (H & 1)) ? lane : lane * 2 + (kk & 1));
 }
 
-// Upper half of the last index word of an odd-degree variable: EDGE_SIG_TAG | 8-bit fingerprint.  Shared memory has
-// fewer than 0xFF00 words, so no absolute slot address reaches the tag (the kernels add their E base to slot halves only).
-constexpr uint32_t EDGE_SIG_TAG = 0xFF00u;
+// Upper half of the last index word of an odd-degree variable in a fast-path slice: EDGE_SIG_TAG | 8-bit fingerprint
+// (0xFE00 .. 0xFEFF).  Shared memory has fewer than 0xFE00 words, so no absolute slot address reaches the tag (the
+// kernels add their E base to slot halves only); an unused half stays 0xFFFF.
+constexpr uint32_t EDGE_SIG_TAG = 0xFE00u;
 
 struct EdgeLayout {
     bool ok = false;

@@ -14,6 +14,18 @@ __device__ __forceinline__ float min_xorsign_abs(float a, float b)
     return d;
 }
 
+// if (v < 0) { a ^= x; b |= y; } as two predicated instructions (the compiler's own form is a select + a logic op each)
+__device__ __forceinline__ void xor_or_if_negative(float v, uint32_t &a, uint32_t x, uint32_t &b, uint32_t y)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %2, 0f00000000;\n\t@p xor.b32 %0, %0, %3;\n\t@p or.b32 %1, %1, %4;\n\t}"
+        : "+r"(a), "+r"(b) : "f"(v), "r"(x), "r"(y));
+}
+
+__device__ __forceinline__ void or_if_negative(float v, uint32_t &b, uint32_t y)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(b) : "f"(v), "r"(y));
+}
+
 // ---- phase A: one row slice, K chunks of 4 edges per lane held in registers -------------------------------
 template <int K, bool FIRST>
 __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_unit, int stride, int lane,
@@ -138,6 +150,8 @@ struct ColCtx {
     uint32_t fp;            // XOR of the fingerprints of the variables whose hard decision is 1
     uint32_t fpw;           // same for the variables whose fingerprint sits in the upper half of an index word (SIGW): bits 16-23
     uint32_t myhw;          // lane j keeps the hard-decision word of the warp's j-th task
+    uint32_t negbits;       // SIGW kernels instead: bit j = hard decision of the lane's variable in the warp's j-th task (the words
+    uint32_t ubit;          // are formed by ballots only when somebody reads them); ubit = 1 << (next task - first task), warp-uniform
     uint32_t t4;            // 4 * next task: byte offset of its prior, compared with lane_t4 to pick the lane that keeps its hard-decision word
     uint32_t lane_t4;       // 4 * (first task of the warp + lane)
     int lane;
@@ -176,14 +190,17 @@ __device__ __forceinline__ void group_load_idx(const ColCtx &c, int g, uint32_t 
     for (int j = 0; j < N; ++j) load_idx_words<D>(c, g * N + j, w[j]);
 }
 
-template <int D, int N>
+template <int D, int N, bool SIGW>
 __device__ __forceinline__ void group_gather(const uint32_t (&w)[N][(D + 1) / 2 + 1], ColGroup<D, N> &G, uint32_t win)
 {
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            G.addr[j][k] = ((k & 1) ? ((w[j][k >> 1] >> 14) & 0x3FFFCu) : ((w[j][k >> 1] << 2) & 0x3FFFCu)) | win;
+            if (SIGW && (D & 1) && k == D - 1)       // tagged last word of an odd degree: byte address | fingerprint << 24
+                G.addr[j][k] = w[j][k >> 1] & 0x3FFFCu;
+            else
+                G.addr[j][k] = ((k & 1) ? ((w[j][k >> 1] >> 14) & 0x3FFFCu) : ((w[j][k >> 1] << 2) & 0x3FFFCu)) | win;
             G.r[j][k] = lds_f32(G.addr[j][k]);
         }
 }
@@ -213,10 +230,14 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const bool neg = v[j] < 0.f;                       // kernels.py:349
-        if constexpr (SIGW && (D & 1)) { if (neg) c.fpw ^= w[j][(D + 1) / 2 - 1]; }       // (unshifted: the caller takes bits 16-23)
+        if constexpr (SIGW && (D & 1)) xor_or_if_negative(v[j], c.fpw, w[j][(D + 1) / 2 - 1], c.negbits, c.ubit << j);   // (fingerprint: bits 24-31)
         else { if (neg) c.fp ^= lds_u8(c.sg + 8 * c.t4 + 32 * j); }
-        const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
-        if (c.lane_t4 == c.t4 + 4 * j) c.myhw = hw;
+        if constexpr (SIGW) {
+            if constexpr (!(D & 1)) or_if_negative(v[j], c.negbits, c.ubit << j);
+        } else {
+            const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
+            if (c.lane_t4 == c.t4 + 4 * j) c.myhw = hw;
+        }
         if constexpr (WRITE_V) {
             static_assert(N == 1, "posterior output assumes one slice per group");
             const uint32_t vid = c.vid_next;                // loaded one task ahead: the store does not wait on it
@@ -226,6 +247,7 @@ __device__ __forceinline__ void group_finish(ColCtx &c, const ColGroup<D, N> &G,
         }
     }
     c.ix += N * ((D + 1) / 2) * 128; c.t4 += 4 * N;
+    if constexpr (SIGW) c.ubit <<= N;
 }
 
 // any slice: partial with a negative prior, per-lane priors, large degree (meta = degree << 16 | lanes << 22)
@@ -253,6 +275,8 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
     }
     const uint32_t hw = __ballot_sync(0xFFFFFFFFu, neg);
     if (c.lane_t4 == c.t4) c.myhw = hw;
+    if (neg) c.negbits |= c.ubit;
+    c.ubit <<= 1;
     if (WRITE_V) { c.vid += 32; c.vid_next = __ldg(c.vid); }
     c.ix += H * 128; c.t4 += 4;
 }
@@ -273,7 +297,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
         uint32_t w[N][(D + 1) / 2 + 1];
         ColGroup<D, N> G;
         group_load_idx<D, N>(c, 0, w);
-        group_gather<D, N>(w, G, c.win);
+        group_gather<D, N, SIGW>(w, G, c.win);
         group_finish<D, EXACT, WRITE_V, N, SIGW>(c, G, pri, w);
     }
     if constexpr (N == 2) {
@@ -281,7 +305,7 @@ __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &
             uint32_t w[1][(D + 1) / 2 + 1];
             ColGroup<D, 1> G;
             group_load_idx<D, 1>(c, 0, w);
-            group_gather<D, 1>(w, G, c.win);
+            group_gather<D, 1, SIGW>(w, G, c.win);
             group_finish<D, EXACT, WRITE_V, 1, SIGW>(c, G, pri, w);
         }
     }

@@ -74,10 +74,11 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
     // slot indices become absolute shared word addresses (E base folded in), so that a gather address is one
     // shift + one mask away from the packed pair
     const uint32_t e_word = (uint32_t)__cvta_generic_to_shared(E) >> 2;
-    // (an upper half >= EDGE_SIG_TAG is the fingerprint of an odd-degree variable, not a slot)
+    // (an upper half EDGE_SIG_TAG | f is the fingerprint f of an odd-degree variable, not a slot,
+    // and its lower half becomes a byte address: byte address | fingerprint << 24)
     for (int i = tid; i < eg.idx_words; i += THREADS) {
         const uint32_t w = eg.col_idx[i];
-        idx[i] = w + ((w >> 16) >= EDGE_SIG_TAG ? e_word : (e_word | (e_word << 16)));
+        idx[i] = (w >> 24) == (EDGE_SIG_TAG >> 8) ? ((((w & 0xFFFFu) + e_word) << 2) | (w >> 16 << 24)) : w + (e_word | (e_word << 16));
     }
     for (int i = tid; i < eg.n_csl; i += THREADS) {
         const uint2 d = eg.ctask[i];
@@ -134,6 +135,17 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
 
         bool conv = false;
         int fin = a.max_iter - 1;
+        // hard decision of the last variable phase: bit j of lane l = variable l of the warp's j-th column slice.  The
+        // words of hperm are formed (one ballot per slice) only when they are read: on a fingerprint match and at the end
+        uint32_t negbits = 0u;
+        auto publish_hperm = [&]() {
+            uint32_t mine = 0u;
+            for (int s = 0; s < c1 - c0; ++s) {
+                const uint32_t hw = __ballot_sync(0xFFFFFFFFu, (negbits >> s) & 1u);
+                if (lane == s) mine = hw;
+            }
+            if (lane < c1 - c0) hperm[c0 + lane] = mine;
+        };
         for (int it = 0; it < a.max_iter; ++it) {
             // ---- phase A --------------------------------------------------------------------------------
             const float alpha = it < 128 ? s_alpha[it] : a.alpha_d[it];
@@ -160,7 +172,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.ix = ix0;
             c.lane4 = lane * 4; c.lane8 = lane * 8;
             c.sg = (uint32_t)__cvta_generic_to_shared(csig + lane);
-            c.fp = 0u; c.fpw = 0u; c.myhw = 0u;
+            c.fp = 0u; c.fpw = 0u; c.myhw = 0u; c.negbits = 0u; c.ubit = 1u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
             c.vid = eg.var_id + c0 * 32 + lane;
             c.vid_next = write_v ? __ldg(c.vid) : 0u;
@@ -170,8 +182,8 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             if (write_v) phase_b<true, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
             else phase_b<false, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
 #endif
-            if (lane < c1 - c0) hperm[c0 + lane] = c.myhw;
-            const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp ^ (c.fpw >> 16)) & 0xFFu;   // (bits 8+: tags of the in-word fingerprints)
+            negbits = c.negbits;
+            const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp ^ (c.fpw >> 24)) & 0xFFu;
             if (lane == 0 && fp) atomicXor(&s_fp[it & 1], fp);
             PROF_T(t3);
             __syncthreads();
@@ -180,6 +192,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             PROF_ADD(0, t1 - t0); PROF_ADD(1, t2 - t1); PROF_ADD(2, t3 - t2); PROF_ADD(3, t4 - t3);
             // ---- convergence: fingerprint of H.hard against the syndrome's, exact test only on a match -----
             if (s_fp[it & 1] == target) {                                              // uniform
+                publish_hperm();
                 parity_of_hard(eg, hperm, cmeta, par, s_plist, &s_pcount, tid, THREADS);
                 __syncthreads();
                 if (warp == 0) { const int w = residual_weight(par, syn, eg.n_rsl, lane); if (lane == 0) s_wt = w; }
@@ -191,6 +204,7 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
         // of its residual syndrome (OSD scheduling hint).  Both walk the variables whose hard decision is 1: their
         // (slice, lane) pairs are listed once, then every (variable, edge) pair and every variable id gets a thread.
         const bool need_wt = !conv && a.max_iter > 0 && a.fail_wt != nullptr;
+        publish_hperm();
         for (int w = tid; w < eg.nw; w += THREADS) hnat[w] = 0u;
         if (tid == 0) { s_target = 0u; s_pcount = 0; }
         __syncthreads();
