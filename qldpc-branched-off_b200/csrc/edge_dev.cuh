@@ -26,6 +26,9 @@ struct EdgeDev {
     const uint4 *wc_cls;         // [nwarps] 16 x u8 slices per class
     const uint32_t *row_mask;    // [n_rsl*32]
     const uint32_t *col_sig;     // [n_csl*32]
+    // byte offsets of the float32 kernel's shared-memory arrays behind E (minsum_edge.cu; precomputed so that the kernel
+    // does not re-derive a chain of eight array sizes every time it needs one of the addresses)
+    uint32_t o_idx, o_rtask, o_syn, o_par, o_hperm, o_hnat, o_cmeta, o_csig;
 };
 
 // ---- phase B ---------------------------------------------------------------------------------------------

@@ -54,15 +54,16 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
                    const __grid_constant__ EdgePriors pri)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // (array offsets: edge_smem_offsets() on the host)
     float *E = reinterpret_cast<float *>(smem_raw);                                   // [e_words]
-    uint32_t *idx = reinterpret_cast<uint32_t *>(E + eg.e_words);                     // [idx_words]
-    uint2 *rtask = reinterpret_cast<uint2 *>(idx + eg.idx_words);                     // [n_rsl]
-    uint32_t *syn = reinterpret_cast<uint32_t *>(rtask + eg.n_rsl);                   // [n_rsl] permuted syndrome bits
-    uint32_t *par = syn + eg.n_rsl;                                                   // [n_rsl] parity of the hard decision
-    uint32_t *hperm = par + eg.n_rsl;                                                 // [n_csl] hard decision word per column slice
-    uint32_t *hnat = hperm + eg.n_csl;                                                // [nw] hard decision, natural order
-    uint32_t *cmeta = hnat + eg.nw;                                                   // [n_csl] degree / lanes of every column slice
-    uint8_t *csig = reinterpret_cast<uint8_t *>(cmeta + eg.n_csl);                    // [n_csl*32] 8-bit fingerprint per variable
+    uint32_t *idx = reinterpret_cast<uint32_t *>(smem_raw + eg.o_idx);                // [idx_words]
+    uint2 *rtask = reinterpret_cast<uint2 *>(smem_raw + eg.o_rtask);                  // [n_rsl]
+    uint32_t *syn = reinterpret_cast<uint32_t *>(smem_raw + eg.o_syn);                // [n_rsl] permuted syndrome bits
+    uint32_t *par = reinterpret_cast<uint32_t *>(smem_raw + eg.o_par);                // [n_rsl] parity of the hard decision
+    uint32_t *hperm = reinterpret_cast<uint32_t *>(smem_raw + eg.o_hperm);            // [n_csl] hard decision word per column slice
+    uint32_t *hnat = reinterpret_cast<uint32_t *>(smem_raw + eg.o_hnat);              // [nw] hard decision, natural order
+    uint32_t *cmeta = reinterpret_cast<uint32_t *>(smem_raw + eg.o_cmeta);            // [n_csl] degree / lanes of every column slice
+    uint8_t *csig = smem_raw + eg.o_csig;                                             // [n_csl*32] 8-bit fingerprint per variable
     __shared__ int s_wt, s_next, s_pcount;
     __shared__ uint16_t s_plist[PAR_LIST_CAP];
     __shared__ float s_alpha[128];                                                    // alpha schedule (first 128 iterations)
@@ -174,13 +175,17 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
             c.sg = (uint32_t)__cvta_generic_to_shared(csig + lane);
             c.fp = 0u; c.fpw = 0u; c.myhw = 0u; c.negbits = 0u; c.ubit = 1u;
             c.t4 = 4u * (uint32_t)c0; c.lane_t4 = 4u * (uint32_t)(c0 + lane); c.lane = lane;
-            c.vid = eg.var_id + c0 * 32 + lane;
-            c.vid_next = write_v ? __ldg(c.vid) : 0u;
-            c.post = a.post ? a.post + (size_t)shot * eg.n : nullptr;
             c.win = 0u;
 #ifndef QB_EDGE_SKIP_B
-            if (write_v) phase_b<true, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
-            else phase_b<false, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            if (write_v) {                                                             // (posterior output: last iteration only in the pipeline)
+                c.vid = eg.var_id + c0 * 32 + lane;
+                c.vid_next = __ldg(c.vid);
+                c.post = a.post + (size_t)shot * eg.n;
+                phase_b<true, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            } else {
+                c.vid = nullptr; c.vid_next = 0u; c.post = nullptr;
+                phase_b<false, true>(c, cls, c1, cmeta, eg.lane_prior, pri);
+            }
 #endif
             negbits = c.negbits;
             const uint32_t fp = __reduce_xor_sync(0xFFFFFFFFu, c.fp ^ (c.fpw >> 24)) & 0xFFu;
@@ -344,6 +349,9 @@ int edge_plan_create(const qb_decoder *dec, const float *prior_h, EdgePlan **out
     EdgeDev &d = p->dev;
     d.n_rsl = L.n_rsl; d.n_csl = L.n_csl; d.e_words = L.e_words; d.e_dummy = L.e_dummy; d.idx_words = L.idx_words;
     d.nw = g.nw; d.n = g.n; d.mw = g.mw;
+    d.o_idx = (uint32_t)L.e_words * 4; d.o_rtask = d.o_idx + (uint32_t)L.idx_words * 4; d.o_syn = d.o_rtask + (uint32_t)L.n_rsl * 8;
+    d.o_par = d.o_syn + (uint32_t)L.n_rsl * 4; d.o_hperm = d.o_par + (uint32_t)L.n_rsl * 4; d.o_hnat = d.o_hperm + (uint32_t)L.n_csl * 4;
+    d.o_cmeta = d.o_hnat + (uint32_t)g.nw * 4; d.o_csig = d.o_cmeta + (uint32_t)L.n_csl * 4;       // (the order edge_smem_bytes() adds up)
     int rc = QB_OK;
     const std::vector<float> e0 = edge_E0(L, prior_h);
     const float *pf = nullptr; const uint32_t *pu = nullptr; const uint16_t *ph = nullptr; const int32_t *pi = nullptr;
