@@ -139,7 +139,11 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     }
     {
         std::vector<int> cost(csl.size());
-        for (size_t i = 0; i < csl.size(); ++i) cost[i] = (csl[i].deg * 8 + 8) * (csl[i].cls == 15 ? 2 : 1);
+        // fast-path cost of a slice of degree D = max(instructions, 4 x shared-memory instructions) of its loop body in
+        // the float32 kernel (odd degrees carry the fingerprint in the index word and are cheaper)
+        static const int fast_cost[9] = {10, 16, 25, 28, 40, 48, 60, 64, 76};
+        for (size_t i = 0; i < csl.size(); ++i)
+            cost[i] = csl[i].cls == 15 ? (csl[i].deg * 8 + 8) * 2 : fast_cost[std::min(8, csl[i].deg)] + (csl[i].exact ? csl[i].deg : 0);
         // (cutting the class-sorted list into contiguous equal-cost pieces -- long runs of one class per warp -- was measured
         // 1.5 % slower than the LPT mix)
         auto sched = lpt(cost, nwarps);
