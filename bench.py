@@ -305,7 +305,8 @@ def main():
                               osd_order=0, alpha_mode="dynamical", base_seed=seed, precomputed_matrices=M, progress=False, **bb)
         dt_pre = time.perf_counter() - t0
         e2e_rs = {"value": n_rs / dt_all, "unit": "shots/s", "shots": n_rs, "seconds": dt_all,
-                  "with_precomputed_matrices": {"value": n_rs / dt_pre, "seconds": dt_pre},
+                  "with_precomputed_matrices": {"value": n_rs / dt_pre, "seconds": dt_pre,
+                                                "note": "second call in the process: decoding matrices passed in, circuit tables from the in-process cache"},
                   "logical_error_rate": res["logical_error_rate"], "same_result_both_calls": res == res2,
                   "path": "qldpc_b200.simulation.engine.run_simulation(num_trials=2**20, maxIter=20, alpha_mode='dynamical', osd_order=0): "
                           "wall clock of the whole call incl. host-side table build and handle creation"}

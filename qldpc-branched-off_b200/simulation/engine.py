@@ -167,6 +167,30 @@ def _alpha_setup(alpha_mode, use_dynamic_alpha, alvarado_alpha, matrices, llrs_z
     raise ValueError(f"Unsupported alpha_mode: {alpha_mode}")
 
 
+_TABLE_CACHE = {}
+
+
+def _circuit_tables(Hx, Hz, Lx, Lz, num_cycles, bb_params):
+    """Compiled circuit + fault signature tables of a code.  They depend on the code and the number of cycles only, not on
+    the error rate, so a sweep over error rates (the reference's main.py:95-141 loop) builds them once per process
+    (0.85 s for the gross code); the last four codes are kept."""
+    import hashlib
+    h = hashlib.sha1()
+    for a in (Hx, Hz, Lx, Lz):
+        a = np.ascontiguousarray(a)
+        h.update(str(a.shape).encode()); h.update(str(a.dtype).encode()); h.update(a.tobytes())
+    h.update(repr((int(num_cycles), sorted((k, np.asarray(v).tolist()) for k, v in bb_params.items()))).encode())
+    key = h.hexdigest()
+    hit = _TABLE_CACHE.pop(key, None)
+    if hit is None:
+        compiled = CompiledCircuit.from_builder(BBCodeCircuit(Hx, Hz, num_cycles=num_cycles, **bb_params))
+        hit = (compiled, fault_tables_for(compiled, Lx, Lz))
+    _TABLE_CACHE[key] = hit                                  # (re-inserted last: the dict is the LRU order)
+    while len(_TABLE_CACHE) > 4:
+        _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
+    return hit
+
+
 def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, maxIter=50, osd_order=0,
                    use_dynamic_alpha=True, alpha_mode=None, alvarado_alpha=None, alpha_estimation_trials=5000,
                    alpha_estimation_bins=50, precomputed_matrices=None, num_workers=None, base_seed=None,
@@ -176,9 +200,7 @@ def run_simulation(Hx, Hz, Lx, Lz, error_rate, num_trials=1000, num_cycles=12, m
         base_seed = np.random.randint(0, 2 ** 31)
     if alpha_mode not in (None, "dynamical", "alvarado", "alvarado-autoregressive"):
         raise ValueError(f"Unsupported alpha_mode: {alpha_mode}")
-    cb = BBCodeCircuit(Hx, Hz, num_cycles=num_cycles, **bb_params)
-    compiled = CompiledCircuit.from_builder(cb)
-    ft = fault_tables_for(compiled, Lx, Lz)
+    compiled, ft = _circuit_tables(Hx, Hz, Lx, Lz, num_cycles, bb_params)
     matrices = precomputed_matrices or matrices_from_tables(ft, error_rate, num_cycles)
     if estimation_plot_dir is not None:
         import os

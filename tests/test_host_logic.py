@@ -316,3 +316,23 @@ def test_sampler_jump_table():
         np.testing.assert_allclose(T[1:] / 2.0 ** 32, (1 - p) ** k, rtol=0, atol=2.0 ** -32 * 1.5)
     with pytest.raises(ValueError):
         _lib.geometric_table(0.0)
+
+
+def test_circuit_tables_are_cached_per_code_and_cycle_count():
+    """run_simulation builds the compiled circuit and the fault signature tables once per (code, cycles) and process: the
+    reference's sweep over error rates (main.py:95-141) calls it once per error rate."""
+    from qldpc_b200.codes.bb_code import make_bb_code
+    from qldpc_b200.simulation import engine
+    code = make_bb_code("[[72, 12, 6]]")
+    bb = {k: code[k] for k in ("ell", "m", "a_x_powers", "a_y_powers", "b_y_powers", "b_x_powers")}
+    engine._TABLE_CACHE.clear()
+    a = engine._circuit_tables(code["Hx"], code["Hz"], code["Lx"], code["Lz"], 3, bb)
+    b = engine._circuit_tables(code["Hx"].copy(), code["Hz"], code["Lx"], code["Lz"], 3, dict(bb))
+    c = engine._circuit_tables(code["Hx"], code["Hz"], code["Lx"], code["Lz"], 2, bb)
+    assert a[0] is b[0] and a[1] is b[1] and c[0] is not a[0] and len(engine._TABLE_CACHE) == 2
+    Lz2 = code["Lz"].copy(); Lz2[0] ^= Lz2[1]
+    d = engine._circuit_tables(code["Hx"], code["Hz"], code["Lx"], Lz2, 3, bb)
+    assert d[1] is not a[1]
+    for cyc in range(4, 9):
+        engine._circuit_tables(code["Hx"], code["Hz"], code["Lx"], code["Lz"], cyc, bb)
+    assert len(engine._TABLE_CACHE) == 4
