@@ -290,7 +290,7 @@ __device__ __forceinline__ void col_task_generic(ColCtx &c, uint32_t meta, const
 template <int D, bool EXACT, bool WRITE_V, bool SIGW>
 __device__ __forceinline__ void col_class(ColCtx &c, int cnt, const EdgePriors &pri)
 {
-    constexpr int N = (D <= 4) ? QB_EDGE_GROUP : 1;
+    constexpr int N = (D <= 4 && !WRITE_V) ? QB_EDGE_GROUP : 1;
     const uint32_t t4_end = c.t4 + 4u * (uint32_t)(cnt / N * N);
 #pragma unroll 1
     while (c.t4 != t4_end) {

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
     const int F = P.a.n_fail_d ? min(*P.a.n_fail_d, P.F) : P.F;
     const int n_in = P.sel_count ? min(min(*P.sel_count, F), P.sel_max) : F;
     const bool second = P.sel_q != nullptr;
+    const bool packed_ok = n <= (1 << 14);                  // column ids fit the 14 bits beside the 17 low key bits
 
     while (true) {
         if (tid == 0) { s_q = atomicAdd(&P.counters[P.sel_counter], 1); s_b1 = SELF_BINS - 1; s_b2 = -1; s_wt = 0; }
@@ -209,7 +210,11 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
                 if (key != 0xFFFFFFFFu && b <= hi) {
                     const uint32_t old = atomicSub(&hist[b], 1u);
                     const int slot = (int)(old >> 16) + (int)(old & 0xFFFFu) - 1;
-                    listK[slot] = key; listI[slot] = (uint16_t)(j0 + u * SELF_THREADS);
+                    const uint32_t j = (uint32_t)(j0 + u * SELF_THREADS);
+                    // inside an unclamped bin the upper 15 bits of the keys agree: (low 17 key bits, 14-bit column) is one
+                    // 31-bit word whose order is the (key, column) order, and the bin number takes the column's place
+                    if (packed_ok && b > 0 && b < SELF_BINS - 1) { listK[slot] = ((key & ((1u << SELF_SHIFT) - 1u)) << 14) | j; listI[slot] = (uint16_t)b; }
+                    else { listK[slot] = key; listI[slot] = (uint16_t)j; }
                 }
             }
         }
@@ -218,7 +223,20 @@ __global__ void __launch_bounds__(SELF_THREADS) osd_select_kernel(const __grid_c
         const long long sp3 = clock64();
 #endif
         uint16_t *out = P.cand + (size_t)oi * P.cap;
+        // the clamped bins sit at the two ends of the list: [0, p_lo) is bin 0, [p_hi, M) the last bin; packed words between
+        const int p_lo = packed_ok ? (hi >= 1 ? (int)(hist[1] >> 16) : M) : M;
+        const int p_hi = hi == SELF_BINS - 1 ? (int)(hist[SELF_BINS - 1] >> 16) : M;
         for (int i = tid; i < M; i += SELF_THREADS) {
+            if (i >= p_lo && i < p_hi) {
+                const uint32_t mine = listK[i];
+                const int b = listI[i];
+                const int lo = (int)(hist[b] >> 16);
+                const int hi2 = b < hi ? (int)(hist[b + 1] >> 16) : M;
+                int rank = lo;
+                for (int k = lo; k < hi2; ++k) rank += listK[k] < mine;
+                out[rank] = (uint16_t)(mine & 0x3FFFu);
+                continue;
+            }
             const uint32_t key = listK[i];
             const uint16_t id = listI[i];
             const int b = self_bin(key);
