@@ -67,10 +67,10 @@ def summarize_clocks(lines):
 
 
 def ncu_traffic(kernel):
-    """Per-launch ncu counters of one kernel from profiles/r2_traffic.json (written by tools/ncu_traffic.py from an
+    """Per-launch ncu counters of one kernel from profiles/r2b_traffic.json (written by tools/ncu_traffic.py from an
     `ncu --set full` capture of this file's own command line; the JSON records the command) -> (dict, shots per launch)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2b_traffic.json")) as f:
             d = json.load(f)
         for name, k in d["kernels"].items():
             if name.startswith(kernel):
@@ -347,7 +347,7 @@ def main():
                          "unit": "GB/s", "frac": em_per_s * 8 / 1e9 / smem_peak,
                          "traffic": (ncu["smem_bytes"] * scale) if ncu else None,
                          "traffic_unit": "bytes/launch: ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum x 128 B of a 16384-shot launch "
-                                         "(profiles/r2_traffic.json), scaled to this launch size",
+                                         "(profiles/r2b_traffic.json), scaled to this launch size",
                          "algorithmic_bytes_per_launch": em_per_launch * 8, "edge_messages_per_launch": em_per_launch,
                          "edge_messages_per_s": em_per_s, "bytes_per_edge_message": 8, "ms_per_launch": ms_launch,
                          "shots_per_launch": shots_per_launch,
@@ -357,7 +357,7 @@ def main():
                                  "(check rows) and by shared-memory instruction issue (variables), DESIGN.md section 4"},
             "roofline_hbm": {"bound": "hbm", "kernel": "minsum_edge_kernel<1024,1>", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "traffic": (ncu["dram_bytes"] * scale) if ncu else None,
-                             "traffic_unit": "bytes/launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r2_traffic.json), scaled",
+                             "traffic_unit": "bytes/launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/r2b_traffic.json), scaled",
                              "algorithmic_bytes_per_launch": hbm_bytes_launch, "peak_source": peak_src,
                              "note": "non-binding by design: messages never leave the SM; traffic = algorithmic bytes (posteriors of non-converged sides), no re-reads"},
             "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,

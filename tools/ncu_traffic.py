@@ -44,7 +44,7 @@ for name, a in acc.items():
     k["smem_bytes"] = k["smem_wavefronts"] * 128.0
     kernels[name] = k
 json.dump({"report": rep, "shots_per_launch": shots,
-           "command": f"ncu --set full --clock-control none --import-source on python bench.py --steps 1 --warmup 1 --no-cpu-baseline --shots-per-step {shots} --batch {shots}",
+           "command": f"tools/ncu_capture.sh: ncu --set full --clock-control none --import-source on -c 18 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-run-simulation --shots-per-step {shots} --batch {shots}",
            "kernels": kernels}, open(out, "w"), indent=1, sort_keys=True)
 for name, k in kernels.items():
     print(f"{name:40s} {k['ms_per_launch']:8.3f} ms  dram {k['dram_bytes']/1e6:9.1f} MB  smem {k['smem_bytes']/1e9:8.2f} GB  inst {k['warp_instructions']/1e6:8.1f} M  issue {k['issue_active_pct']:5.1f}%  warps {k['warps_active_pct']:5.1f}%")
