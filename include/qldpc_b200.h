@@ -87,7 +87,8 @@ int qb_decoder_minsum_path(qb_decoder *dec);
  * every edge chosen so that the 32 gathers of one warp instruction of the variable phase hit 32 different banks.
  * stats_out[16] = { usable, row slices, column slices, edge words, index words, gather instructions per iteration,
  *   shared-memory wavefronts they need (equal when conflict free), edges still in a bank conflict, priors uniform per
- *   slice, max chunks per row, max column degree, every edge owns exactly one slot (self check), 0... }.
+ *   slice, max chunks per row, max column degree, self check (every edge owns exactly one slot; the fingerprint tags
+ *   in the free index halves of odd-degree slices are where and what the kernel expects), 0... }.
  * Replaces nothing in the reference (numba walks CSR arrays, src/decoding/kernels.py:283-345); it is the
  * data-layout step of qb_decoder_create, exposed for tests. */
 int qb_edge_layout_probe(int32_t m, int32_t n, const int32_t *indptr_h, const int32_t *indices_h,

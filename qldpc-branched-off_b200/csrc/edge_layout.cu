@@ -390,6 +390,24 @@ extern "C" int qb_edge_layout_probe(int32_t m, int32_t n, const int32_t *indptr,
             }
     }
     if (cnt != L.nnz) good = false;
+    // odd-degree slices on the fast path carry EDGE_SIG_TAG | fingerprint in the upper half of every lane's last index word
+    // (dummy lanes: fingerprint 0); no other word has an upper half in the tag range
+    for (int t = 0; t < L.n_csl; ++t) {
+        const int base = (int)(L.ctask[2 * t] & 0xFFFFu) * 32, deg = (int)((L.ctask[2 * t] >> 16) & 63u), nl = (int)((L.ctask[2 * t] >> 22) & 63u);
+        const int H = (deg + 1) / 2;
+        // (fast path = what build_edge_layout classified below class 15: full or non-negative prior, uniform priors, degree
+        // <= 8, or <= 6 next to a degree-1 row; recognised here by the tag itself on lane 0)
+        const bool tagged = (deg & 1) && ((L.col_idx[base + qb::edge_idx_off(H, H - 1, 0)] >> 16) & 0xFF00u) == qb::EDGE_SIG_TAG;
+        for (int l = 0; l < 32; ++l)
+            for (int kk = 0; kk < H; ++kk) {
+                const uint32_t hi = L.col_idx[base + qb::edge_idx_off(H, kk, l)] >> 16;
+                const bool in_range = (hi & 0xFF00u) == qb::EDGE_SIG_TAG;
+                if (tagged && kk == H - 1) {
+                    if (hi != (qb::EDGE_SIG_TAG | (l < nl ? (L.col_sig[t * 32 + l] & 0xFFu) : 0u))) good = false;
+                } else if (in_range) good = false;
+            }
+        if ((deg & 1) && deg <= 8 && nl == 32 && L.uniform_prior && !tagged && !((L.ctask[2 * t] >> 28) & 1u)) good = false;   // a full plain slice must be tagged
+    }
     stats_out[11] = good;
     return 0;
 }
