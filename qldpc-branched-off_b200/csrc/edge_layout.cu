@@ -278,7 +278,9 @@ EdgeLayout build_edge_layout(int m, int n, const int32_t *indptr, const int32_t 
     for (int i = L.e_dummy; i < L.e_words; ++i) L.slot_var[i] = -2;
     for (int t = 0; t < L.n_rsl; ++t) {
         const int nl = (int)rsl[t].rows.size();
-        L.rtask[2 * t] = (uint32_t)rs_base[t];
+        bool onepad = rsl[t].K > 0 && rsl[t].K <= 9;
+        for (int r : rsl[t].rows) if (indptr[r + 1] - indptr[r] != 4 * rsl[t].K - 1) onepad = false;
+        L.rtask[2 * t] = (uint32_t)rs_base[t] | (onepad ? 1u : 0u);           // (the base is a multiple of 4 words; bit 0: one unused slot per row)
         L.rtask[2 * t + 1] = (uint32_t)rsl[t].K | ((uint32_t)nl << 8) | ((uint32_t)rs_stride[t] << 16);
         for (int l = 0; l < nl; ++l) {
             const int r = rsl[t].rows[l];

@@ -27,7 +27,8 @@ __device__ __forceinline__ void or_if_negative(float v, uint32_t &b, uint32_t y)
 }
 
 // ---- phase A: one row slice, K chunks of 4 edges per lane held in registers -------------------------------
-template <int K, bool FIRST>
+// ONEPAD: every row of the slice has exactly one unused slot (degree 4K - 1; rtask.x bit 0), so only pads.x's lower half is set
+template <int K, bool FIRST, bool ONEPAD = false>
 __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_unit, int stride, int lane,
                                          uint32_t synsign, float alpha, float clip, uint2 pads)
 {
@@ -58,7 +59,7 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
     const uint32_t tot = (__float_as_uint(m1s) & 0x80000000u) ^ synsign;      // kernels.py:289-298
     // a row of degree 1 (three unused slots in a one-chunk row) has no second edge: its min2 stays +inf
     float clip2 = clip;
-    if constexpr (K == 1) clip2 = ((pads.y & 0xFFFFu) != 0xFFFFu) ? INFINITY : clip;
+    if constexpr (K == 1 && !ONEPAD) clip2 = ((pads.y & 0xFFFFu) != 0xFFFFu) ? INFINITY : clip;
     const float A1 = alpha * fminf(m1, clip), A2 = alpha * fminf(m2, clip2);  // kernels.py:309-314, A1 <= A2
     // Measured alternatives that lost (B200): forming the magnitude on the idle fma pipe (t = |Q| - min1 scaled to
     // -inf unless 0, max(A2 + t, A1)): 6 % slower, the extra issue slots cost more than the alu-pipe relief; moving
@@ -79,9 +80,11 @@ __device__ __forceinline__ void row_task(float *E, const float4 *E0, int base_un
     }
     // unused slots back to +inf (every row has at least one)
     E[pads.x & 0xFFFFu] = INFINITY;
-    if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;
-    if ((pads.y & 0xFFFFu) != 0xFFFFu) E[pads.y & 0xFFFFu] = INFINITY;
-    if ((pads.y >> 16) != 0xFFFFu) E[pads.y >> 16] = INFINITY;
+    if constexpr (!ONEPAD) {
+        if ((pads.x >> 16) != 0xFFFFu) E[pads.x >> 16] = INFINITY;
+        if ((pads.y & 0xFFFFu) != 0xFFFFu) E[pads.y & 0xFFFFu] = INFINITY;
+        if ((pads.y >> 16) != 0xFFFFu) E[pads.y >> 16] = INFINITY;
+    }
 }
 
 // generic row (K > 9): two passes over shared memory
@@ -137,6 +140,25 @@ __device__ __forceinline__ void row_dispatch(float *E, const float4 *E0, int bas
     case 8: row_task<8, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
     case 9: row_task<9, FIRST>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
     default: row_task_loop<FIRST>(E, E0, base_unit, stride, lane, K, synsign, alpha, clip, pads); break;
+    }
+}
+
+// slices whose rows all have exactly one unused slot (most rows of a regular code: the gross code's 792 rows of degree 35)
+template <bool FIRST>
+__device__ __forceinline__ void row_dispatch_onepad(float *E, const float4 *E0, int base_unit, int stride, int lane, int K,
+                                                    uint32_t synsign, float alpha, float clip, uint32_t pad)
+{
+    const uint2 pads = make_uint2(pad, 0xFFFFFFFFu);
+    switch (K) {
+    case 1: row_task<1, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 2: row_task<2, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 3: row_task<3, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 4: row_task<4, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 5: row_task<5, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 6: row_task<6, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 7: row_task<7, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    case 8: row_task<8, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
+    default: row_task<9, FIRST, true>(E, E0, base_unit, stride, lane, synsign, alpha, clip, pads); break;
     }
 }
 

@@ -157,6 +157,12 @@ minsum_edge_kernel(const __grid_constant__ EdgeDev eg, const __grid_constant__ M
                 const int K = d.y & 255, nl = (d.y >> 8) & 255, stride = d.y >> 16;
                 if (K == 0 || lane >= nl) continue;
                 const uint32_t synsign = ((syn[t] >> lane) & 1u) << 31;
+                if (d.x & 1u) {                                                        // exactly one unused slot per row (K <= 9)
+                    const uint32_t pad = __ldg(reinterpret_cast<const uint32_t *>(&eg.row_pads[t * 32 + lane]));
+                    if (it == 0) row_dispatch_onepad<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, INFINITY, pad);
+                    else row_dispatch_onepad<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, a.clip, pad);
+                    continue;
+                }
                 const uint2 pads = __ldg(&eg.row_pads[t * 32 + lane]);
                 if (it == 0) row_dispatch<true>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, INFINITY, pads);
                 else row_dispatch<false>(E, eg.E0, (int)(d.x >> 2), stride, lane, K, synsign, alpha, a.clip, pads);
