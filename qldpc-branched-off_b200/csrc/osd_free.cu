@@ -564,25 +564,33 @@ __global__ void __launch_bounds__(FREE_WARPS_MAX * 32) osd_free_kernel(const __g
             for (int w = lane; w < total; w += 32) stage[w] = ldcg_u32(&rec[off_lo + w]);
             sigbuf[lane] = lane < nch ? g.colsig[mt_l & 0xFFFFu] : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             __syncwarp();
-            for (int j = 0; j < nch; ++j) {
-                const uint32_t mt = __shfl_sync(0xFFFFFFFFu, mt_l, j);
-                const int st0 = __shfl_sync(0xFFFFFFFFu, start_l, j);
-                const int nwr = (int)(mt >> 17), col = (int)(mt & 0xFFFFu);
-                uint32_t par;
-                if (nwr == 0) {
-                    const uint32_t x = stage[st0];
-                    par = (ybits[x >> 5] >> (x & 31)) & 1u;
-                } else {
-                    par = lane < nwr ? (uint32_t)__popc(stage[st0 + lane] & ybits[lane]) : 0u;
-                    for (int w = 32 + lane; w < nwr; w += 32) par ^= (uint32_t)__popc(stage[st0 + w] & ybits[w]);
-                    par = __reduce_xor_sync(0xFFFFFFFFu, par) & 1u;
+            // Lane j evaluates e_j = sigma_j ^ parity(R_j & y) of ITS pivot against the current y; the first pivot (in solve
+            // order) with e = 1 changes y, everything before it is final with e = 0, everything after it is evaluated
+            // again.  Rounds = solution bits in the chunk + 1 (about a quarter of the pivots) instead of one dependent
+            // step per pivot.
+            const int nwr_l = (int)(mt_l >> 17);
+            int p0 = 0;                                                                          // pivots before p0 are settled
+            while (p0 < nch) {
+                uint32_t par = 0u;
+                if (lane >= p0 && lane < nch) {
+                    if (nwr_l == 0) {
+                        const uint32_t x = stage[start_l];
+                        par = (ybits[x >> 5] >> (x & 31)) & 1u;
+                    } else {
+                        for (int w = 0; w < nwr_l; ++w) par ^= (uint32_t)__popc(stage[start_l + w] & ybits[w]);
+                        par &= 1u;
+                    }
+                    par ^= (mt_l >> 16) & 1u;
                 }
-                if ((((mt >> 16) & 1u) ^ par) != 0u) {
-                    if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
-                    const uint32_t r = lane < 8 ? (uint32_t)sig16[j * 8 + lane] : 0xFFFFu;
-                    if (r != 0xFFFFu) { const uint32_t x = rowmap[r]; atomicXor(&ybits[x >> 5], 1u << (x & 31)); }
-                    __syncwarp();
-                }
+                const uint32_t ones = __ballot_sync(0xFFFFFFFFu, par != 0u);
+                if (ones == 0u) break;
+                const int j = __ffs(ones) - 1;
+                const uint32_t col = __shfl_sync(0xFFFFFFFFu, mt_l, j) & 0xFFFFu;
+                if (lane == 0) atomicXor(&hard_rw[col >> 5], 1u << (col & 31));
+                const uint32_t r = lane < 8 ? (uint32_t)sig16[j * 8 + lane] : 0xFFFFu;
+                if (r != 0xFFFFu) { const uint32_t x = rowmap[r]; atomicXor(&ybits[x >> 5], 1u << (x & 31)); }
+                __syncwarp();
+                p0 = j + 1;
             }
             off_hi = off_lo;
         }
